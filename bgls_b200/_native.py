@@ -1,0 +1,158 @@
+"""ctypes binding of the C ABI in include/bgls_b200.h (plumbing only: no arithmetic here).
+
+The library is the product; if it is missing or no CUDA device is usable this module raises --
+there is deliberately no CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libbgls_b200.so")
+
+ALTBN128, BLS12_381 = 0, 1
+G1, G2 = 1, 2
+FP_BYTES = {ALTBN128: 32, BLS12_381: 48}
+
+EXPORTS = [
+    "bgls_ctx_create", "bgls_ctx_destroy", "bgls_last_error", "bgls_version", "bgls_pairing_product", "bgls_pair",
+    "bgls_gt_mul", "bgls_aggregate_points", "bgls_scale_points", "bgls_miller_product", "bgls_final_exp_product",
+    "bgls_pairing_check_batch", "bgls_pairing_product_dev", "bgls_miller_product_dev", "bgls_final_exp_product_dev",
+    "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count",
+]
+
+_lib = None
+
+
+class BglsError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BglsError(f"{LIB_PATH} not built: run `python -m bgls_b200.build` (no CPU fallback exists)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, i, cp = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p
+    ip = ctypes.POINTER(ctypes.c_int)
+    L.bgls_ctx_create.argtypes = [i, ctypes.POINTER(vp)]
+    L.bgls_ctx_destroy.argtypes = [vp]
+    L.bgls_ctx_destroy.restype = None
+    L.bgls_last_error.argtypes = [vp]
+    L.bgls_last_error.restype = ctypes.c_char_p
+    L.bgls_version.restype = ctypes.c_char_p
+    L.bgls_pairing_product.argtypes = [vp, i, cp, cp, sz, cp, ip]
+    L.bgls_pair.argtypes = [vp, i, cp, cp, cp]
+    L.bgls_gt_mul.argtypes = [vp, i, cp, cp, cp]
+    L.bgls_aggregate_points.argtypes = [vp, i, i, cp, sz, cp]
+    L.bgls_scale_points.argtypes = [vp, i, i, cp, cp, sz, cp]
+    L.bgls_miller_product.argtypes = [vp, i, cp, cp, sz, cp]
+    L.bgls_final_exp_product.argtypes = [vp, i, cp, sz, cp, ip]
+    L.bgls_pairing_check_batch.argtypes = [vp, i, cp, cp, ctypes.POINTER(ctypes.c_uint64), sz, cp]
+    L.bgls_pairing_product_dev.argtypes = [vp, i, vp, vp, sz, vp, vp, vp]
+    L.bgls_miller_product_dev.argtypes = [vp, i, vp, vp, sz, vp, vp]
+    L.bgls_final_exp_product_dev.argtypes = [vp, i, vp, sz, vp, vp, vp]
+    L.bgls_aggregate_points_dev.argtypes = [vp, i, i, vp, sz, vp, vp]
+    L.bgls_scale_points_dev.argtypes = [vp, i, i, vp, vp, sz, vp, vp]
+    L.bgls_pairing_check_batch_dev.argtypes = [vp, i, vp, vp, vp, sz, sz, vp, vp]
+    L.bgls_launch_count.argtypes = [vp]
+    L.bgls_launch_count.restype = ctypes.c_uint64
+    _lib = L
+    return L
+
+
+class Context:
+    """One engine context bound to one CUDA device (bgls_ctx)."""
+
+    def __init__(self, device: int = 0):
+        L = load()
+        h = ctypes.c_void_p()
+        rc = L.bgls_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise BglsError(f"bgls_ctx_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+        self._h, self._L, self.device = h, L, device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bgls_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise BglsError(f"bgls error {rc}: {self._L.bgls_last_error(self._h).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.bgls_launch_count(self._h))
+
+    # ---- host-buffer API (bytes in / bytes out)
+    def pairing_product(self, curve, g1: bytes, g2: bytes, n: int):
+        out = ctypes.create_string_buffer(12 * FP_BYTES[curve])
+        flag = ctypes.c_int(0)
+        self._chk(self._L.bgls_pairing_product(self._h, curve, g1, g2, n, out, ctypes.byref(flag)))
+        return out.raw, bool(flag.value)
+
+    def pair(self, curve, g1: bytes, g2: bytes) -> bytes:
+        out = ctypes.create_string_buffer(12 * FP_BYTES[curve])
+        self._chk(self._L.bgls_pair(self._h, curve, g1, g2, out))
+        return out.raw
+
+    def gt_mul(self, curve, a: bytes, b: bytes) -> bytes:
+        out = ctypes.create_string_buffer(12 * FP_BYTES[curve])
+        self._chk(self._L.bgls_gt_mul(self._h, curve, a, b, out))
+        return out.raw
+
+    def aggregate_points(self, curve, group, pts: bytes, n: int) -> bytes:
+        out = ctypes.create_string_buffer(2 * group * FP_BYTES[curve])
+        self._chk(self._L.bgls_aggregate_points(self._h, curve, group, pts, n, out))
+        return out.raw
+
+    def scale_points(self, curve, group, pts: bytes, scalars: bytes, n: int) -> bytes:
+        out = ctypes.create_string_buffer(max(1, n * 2 * group * FP_BYTES[curve]))
+        self._chk(self._L.bgls_scale_points(self._h, curve, group, pts, scalars, n, out))
+        return out.raw[: n * 2 * group * FP_BYTES[curve]]
+
+    def miller_product(self, curve, g1: bytes, g2: bytes, n: int) -> bytes:
+        out = ctypes.create_string_buffer(12 * FP_BYTES[curve])
+        self._chk(self._L.bgls_miller_product(self._h, curve, g1, g2, n, out))
+        return out.raw
+
+    def final_exp_product(self, curve, partials: bytes, k: int):
+        out = ctypes.create_string_buffer(12 * FP_BYTES[curve])
+        flag = ctypes.c_int(0)
+        self._chk(self._L.bgls_final_exp_product(self._h, curve, partials, k, out, ctypes.byref(flag)))
+        return out.raw, bool(flag.value)
+
+    def pairing_check_batch(self, curve, g1: bytes, g2: bytes, offsets) -> list:
+        nb = len(offsets) - 1
+        off = (ctypes.c_uint64 * (nb + 1))(*offsets)
+        out = ctypes.create_string_buffer(max(1, nb))
+        self._chk(self._L.bgls_pairing_check_batch(self._h, curve, g1, g2, off, nb, out))
+        return [bool(b) for b in out.raw[:nb]]
+
+    # ---- device-resident API (raw device pointers + cudaStream_t handles as ints)
+    def pairing_product_dev(self, curve, d_g1, d_g2, n, d_out, d_flag, stream):
+        self._chk(self._L.bgls_pairing_product_dev(self._h, curve, d_g1, d_g2, n, d_out, d_flag, stream))
+
+    def miller_product_dev(self, curve, d_g1, d_g2, n, d_out, stream):
+        self._chk(self._L.bgls_miller_product_dev(self._h, curve, d_g1, d_g2, n, d_out, stream))
+
+    def final_exp_product_dev(self, curve, d_partials, k, d_out, d_flag, stream):
+        self._chk(self._L.bgls_final_exp_product_dev(self._h, curve, d_partials, k, d_out, d_flag, stream))
+
+    def aggregate_points_dev(self, curve, group, d_pts, n, d_out, stream):
+        self._chk(self._L.bgls_aggregate_points_dev(self._h, curve, group, d_pts, n, d_out, stream))
+
+    def scale_points_dev(self, curve, group, d_pts, d_sc, n, d_out, stream):
+        self._chk(self._L.bgls_scale_points_dev(self._h, curve, group, d_pts, d_sc, n, d_out, stream))
+
+    def pairing_check_batch_dev(self, curve, d_g1, d_g2, d_off, nbatch, total, d_ok, stream):
+        self._chk(self._L.bgls_pairing_check_batch_dev(self._h, curve, d_g1, d_g2, d_off, nbatch, total, d_ok, stream))

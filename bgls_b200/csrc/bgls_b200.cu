@@ -1,0 +1,533 @@
+// bgls_b200: CUDA kernels (sm_100a) and the C ABI declared in include/bgls_b200.h.
+//
+// Kernel inventory:
+//   k_miller_product   K1+K2  one Miller loop per thread, per-block Fp12 product tree in SMEM
+//   k_finish           K2+K3  product of the per-block partials, one final exponentiation
+//   k_miller_values / k_batch_finish   throughput mode: many independent products per launch
+//   k_aggregate / k_aggregate_finish   K4  n-way G1/G2 sum (AggregatePoints)
+//   k_scale            ScalePoints (Point.Mul)
+// There is no CPU fallback: without a CUDA device bgls_ctx_create fails with BGLS_ERR_NODEV.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/bgls_b200.h"
+#include "pairing.cuh"
+
+namespace bgls {
+
+constexpr int TB = 32;        // threads per block, thread-per-item kernels
+constexpr int MAX_BLOCKS = 148 * 16;
+
+// ---------------------------------------------------------------- block-wide Fp12 product
+template <class C> __device__ void block_product(Fp12<C>& acc, Fp12<C>* sh) {
+    const int tid = threadIdx.x;
+    sh[tid] = acc;
+    __syncthreads();
+    for (int s = TB / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            fp12_mul(acc, acc, sh[tid + s]);
+            sh[tid] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(TB) k_miller_product(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                       size_t n, Fp12<C>* __restrict__ partial) {
+    __shared__ Fp12<C> sh[TB];
+    Fp12<C> acc;
+    fp12_one(acc);
+    bool first = true;
+    for (size_t i = (size_t)blockIdx.x * TB + threadIdx.x; i < n; i += (size_t)gridDim.x * TB) {
+        G1Aff<C> P;
+        G2Aff<C> Q;
+        g1_load<C>(P, g1 + i * 2 * C::FP_BYTES);
+        g2_load<C>(Q, g2 + i * 4 * C::FP_BYTES);
+        if (first) {
+            miller_loop(acc, P, Q);
+            first = false;
+        } else {
+            Fp12<C> f;
+            miller_loop(f, P, Q);
+            fp12_mul(acc, acc, f);
+        }
+    }
+    block_product(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// one block: multiply k partial values, optionally exponentiate, emit wire bytes + identity flag
+template <class C, bool IN_BYTES>
+__global__ void __launch_bounds__(TB) k_finish(const void* __restrict__ in, size_t k, int do_final,
+                                               uint8_t* __restrict__ out_gt, int* __restrict__ is_identity) {
+    __shared__ Fp12<C> sh[TB];
+    Fp12<C> acc;
+    fp12_one(acc);
+    for (size_t i = threadIdx.x; i < k; i += TB) {
+        Fp12<C> f;
+        if (IN_BYTES) fp12_from_be<C>(f, (const uint8_t*)in + i * 12 * C::FP_BYTES);
+        else f = ((const Fp12<C>*)in)[i];
+        fp12_mul(acc, acc, f);
+    }
+    block_product(acc, sh);
+    if (threadIdx.x == 0) {
+        if (do_final) final_exp(acc, acc);
+        fp12_to_be<C>(out_gt, acc);
+        if (is_identity) *is_identity = fp12_is_one(acc) ? 1 : 0;
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(TB) k_miller_values(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                      size_t n, Fp12<C>* __restrict__ vals) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    G1Aff<C> P;
+    G2Aff<C> Q;
+    Fp12<C> f;
+    g1_load<C>(P, g1 + i * 2 * C::FP_BYTES);
+    g2_load<C>(Q, g2 + i * 4 * C::FP_BYTES);
+    miller_loop(f, P, Q);
+    vals[i] = f;
+}
+template <class C>
+__global__ void __launch_bounds__(TB) k_batch_finish(const Fp12<C>* __restrict__ vals, const uint64_t* __restrict__ offsets,
+                                                     size_t nbatch, uint8_t* __restrict__ out_ok) {
+    const size_t b = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (b >= nbatch) return;
+    Fp12<C> acc;
+    fp12_one(acc);
+    for (uint64_t i = offsets[b]; i < offsets[b + 1]; i++) fp12_mul(acc, acc, vals[i]);
+    final_exp(acc, acc);
+    out_ok[b] = fp12_is_one(acc) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- point aggregation / scaling
+template <class C, class F>
+__global__ void __launch_bounds__(TB) k_aggregate(const uint8_t* __restrict__ pts, size_t n, size_t rec,
+                                                  Jac<F>* __restrict__ partial) {
+    __shared__ Jac<F> sh[TB];
+    Jac<F> acc;
+    acc.inf = true;
+    for (size_t i = (size_t)blockIdx.x * TB + threadIdx.x; i < n; i += (size_t)gridDim.x * TB) {
+        Jac<F> p;
+        jac_load<C>(p, pts + i * rec);
+        jac_add(acc, acc, p);
+    }
+    const int tid = threadIdx.x;
+    sh[tid] = acc;
+    __syncthreads();
+    for (int s = TB / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            jac_add(acc, acc, sh[tid + s]);
+            sh[tid] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) partial[blockIdx.x] = acc;
+}
+template <class C, class F>
+__global__ void __launch_bounds__(TB) k_aggregate_finish(const Jac<F>* __restrict__ partial, size_t k, uint8_t* __restrict__ out) {
+    __shared__ Jac<F> sh[TB];
+    Jac<F> acc;
+    acc.inf = true;
+    for (size_t i = threadIdx.x; i < k; i += TB) jac_add(acc, acc, partial[i]);
+    const int tid = threadIdx.x;
+    sh[tid] = acc;
+    __syncthreads();
+    for (int s = TB / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            jac_add(acc, acc, sh[tid + s]);
+            sh[tid] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) jac_store<C>(out, acc);
+}
+template <class C, class F>
+__global__ void __launch_bounds__(TB) k_scale(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, size_t n,
+                                              size_t rec, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    Jac<F> p, r;
+    jac_load<C>(p, pts + i * rec);
+    jac_mul(r, p, scalars + 32 * i);
+    jac_store<C>(out + i * rec, r);
+}
+
+}  // namespace bgls
+
+// ==================================================================== host side / C ABI
+using namespace bgls;
+
+struct bgls_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    uint64_t launches = 0;
+    std::mutex mu;
+    std::string err;
+};
+
+namespace {
+
+const char* kVersion = "bgls_b200 r1 sm_100a";
+
+int fail(bgls_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (e != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define CU(call)                                                         \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return fail(ctx, BGLS_ERR_CUDA, #call, e__); \
+    } while (0)
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int ensure_scratch(bgls_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return BGLS_OK;
+    // the old buffer may still be in use by work enqueued earlier
+    CU(cudaDeviceSynchronize());
+    if (ctx->scratch) CU(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t want = align_up(bytes + bytes / 4, 1 << 20);
+    CU(cudaMalloc(&ctx->scratch, want));
+    ctx->scratch_bytes = want;
+    return BGLS_OK;
+}
+int blocks_for(size_t n) {
+    size_t b = (n + TB - 1) / TB;
+    if (b < 1) b = 1;
+    if (b > (size_t)MAX_BLOCKS) b = MAX_BLOCKS;
+    return (int)b;
+}
+bool curve_ok(int c) { return c == BGLS_ALTBN128 || c == BGLS_BLS12_381; }
+size_t fp_bytes(int c) { return c == BGLS_ALTBN128 ? 32 : 48; }
+size_t fp12_dev_bytes(int c) { return c == BGLS_ALTBN128 ? sizeof(Fp12<BN254>) : sizeof(Fp12<BLS381>); }
+size_t jac_dev_bytes(int c, int g) {
+    if (c == BGLS_ALTBN128) return g == 1 ? sizeof(Jac<Fp<BN254>>) : sizeof(Jac<Fp2<BN254>>);
+    return g == 1 ? sizeof(Jac<Fp<BLS381>>) : sizeof(Jac<Fp2<BLS381>>);
+}
+
+// ---- enqueue helpers (device pointers); `work` is device scratch owned by the caller
+template <class C>
+int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final, uint8_t* d_out,
+                    int* d_flag, void* work, cudaStream_t s) {
+    const int nb = blocks_for(n);
+    Fp12<C>* partial = (Fp12<C>*)work;
+    if (n > 0) {
+        k_miller_product<C><<<nb, TB, 0, s>>>(d_g1, d_g2, n, partial);
+        ctx->launches++;
+    }
+    k_finish<C, false><<<1, TB, 0, s>>>(partial, n > 0 ? (size_t)nb : 0, do_final, d_out, d_flag);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+template <class C, class F>
+int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, size_t rec, uint8_t* d_out, void* work, cudaStream_t s) {
+    const int nb = blocks_for(n);
+    Jac<F>* partial = (Jac<F>*)work;
+    k_aggregate<C, F><<<nb, TB, 0, s>>>(d_pts, n, rec, partial);
+    k_aggregate_finish<C, F><<<1, TB, 0, s>>>(partial, nb, d_out);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+
+int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
+                void* d_flag, void* work, cudaStream_t s) {
+    if (curve == BGLS_ALTBN128)
+        return enqueue_pairing<BN254>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+    return enqueue_pairing<BLS381>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+}
+int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, cudaStream_t s) {
+    if (curve == BGLS_ALTBN128) k_finish<BN254, true><<<1, TB, 0, s>>>(d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag);
+    else k_finish<BLS381, true><<<1, TB, 0, s>>>(d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+int aggregate_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* work, cudaStream_t s) {
+    const size_t rec = 2 * group * fp_bytes(curve);
+    const uint8_t* p = (const uint8_t*)d_pts;
+    uint8_t* o = (uint8_t*)d_out;
+    if (curve == BGLS_ALTBN128) {
+        if (group == 1) return enqueue_aggregate<BN254, Fp<BN254>>(ctx, p, n, rec, o, work, s);
+        return enqueue_aggregate<BN254, Fp2<BN254>>(ctx, p, n, rec, o, work, s);
+    }
+    if (group == 1) return enqueue_aggregate<BLS381, Fp<BLS381>>(ctx, p, n, rec, o, work, s);
+    return enqueue_aggregate<BLS381, Fp2<BLS381>>(ctx, p, n, rec, o, work, s);
+}
+int scale_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void* d_sc, size_t n, void* d_out, cudaStream_t s) {
+    const size_t rec = 2 * group * fp_bytes(curve);
+    const uint8_t *p = (const uint8_t*)d_pts, *sc = (const uint8_t*)d_sc;
+    uint8_t* o = (uint8_t*)d_out;
+    const int nb = (int)((n + TB - 1) / TB);
+    if (n == 0) return BGLS_OK;
+    if (curve == BGLS_ALTBN128) {
+        if (group == 1) k_scale<BN254, Fp<BN254>><<<nb, TB, 0, s>>>(p, sc, n, rec, o);
+        else k_scale<BN254, Fp2<BN254>><<<nb, TB, 0, s>>>(p, sc, n, rec, o);
+    } else {
+        if (group == 1) k_scale<BLS381, Fp<BLS381>><<<nb, TB, 0, s>>>(p, sc, n, rec, o);
+        else k_scale<BLS381, Fp2<BLS381>><<<nb, TB, 0, s>>>(p, sc, n, rec, o);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
+              void* d_ok, void* work, cudaStream_t s) {
+    const int nb1 = (int)((total + TB - 1) / TB), nb2 = (int)((nbatch + TB - 1) / TB);
+    if (curve == BGLS_ALTBN128) {
+        if (total) k_miller_values<BN254><<<nb1, TB, 0, s>>>((const uint8_t*)d_g1, (const uint8_t*)d_g2, total, (Fp12<BN254>*)work);
+        if (nbatch) k_batch_finish<BN254><<<nb2, TB, 0, s>>>((const Fp12<BN254>*)work, (const uint64_t*)d_off, nbatch, (uint8_t*)d_ok);
+    } else {
+        if (total) k_miller_values<BLS381><<<nb1, TB, 0, s>>>((const uint8_t*)d_g1, (const uint8_t*)d_g2, total, (Fp12<BLS381>*)work);
+        if (nbatch) k_batch_finish<BLS381><<<nb2, TB, 0, s>>>((const Fp12<BLS381>*)work, (const uint64_t*)d_off, nbatch, (uint8_t*)d_ok);
+    }
+    ctx->launches += (total ? 1 : 0) + (nbatch ? 1 : 0);
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+
+struct Guard {
+    bgls_ctx* c;
+    explicit Guard(bgls_ctx* ctx) : c(ctx) { c->mu.lock(); }
+    ~Guard() { c->mu.unlock(); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* bgls_version(void) { return kVersion; }
+
+int bgls_ctx_create(int device, bgls_ctx** out) {
+    if (!out) return BGLS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BGLS_ERR_NODEV;
+    bgls_ctx* ctx = new bgls_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return BGLS_ERR_CUDA;
+    }
+    *out = ctx;
+    return BGLS_OK;
+}
+void bgls_ctx_destroy(bgls_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* bgls_last_error(const bgls_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t bgls_launch_count(const bgls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- host-buffer entry points
+static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, int do_final,
+                        uint8_t* out, int* flag) {
+    if (!ctx || !curve_ok(curve) || !out || (n && (!g1 || !g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), b1 = align_up(n * 2 * F), b2 = align_up(n * 4 * F), bo = align_up(12 * F + 16);
+    const size_t bw = align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
+    int rc = ensure_scratch(ctx, b1 + b2 + bo + bw);
+    if (rc) return rc;
+    uint8_t* base = (uint8_t*)ctx->scratch;
+    uint8_t *d1 = base, *d2 = base + b1, *dout = base + b1 + b2, *work = dout + bo;
+    int* dflag = (int*)(dout + 12 * F);
+    if (n) {
+        CU(cudaMemcpyAsync(d1, g1, n * 2 * F, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d2, g2, n * 4 * F, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = pairing_dev(ctx, curve, d1, d2, n, do_final, dout, dflag, work, ctx->stream);
+    if (rc) return rc;
+    uint8_t hbuf[12 * 48 + 16];
+    CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, hbuf, 12 * F);
+    if (flag) memcpy(flag, hbuf + 12 * F, 4);
+    return BGLS_OK;
+}
+int bgls_pairing_product(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out_gt, int* is_identity) {
+    return pairing_host(ctx, curve, g1, g2, n, 1, out_gt, is_identity);
+}
+int bgls_pair(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, uint8_t* out_gt) {
+    return pairing_host(ctx, curve, g1, g2, 1, 1, out_gt, nullptr);
+}
+int bgls_miller_product(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out_f) {
+    return pairing_host(ctx, curve, g1, g2, n, 0, out_f, nullptr);
+}
+int bgls_final_exp_product(bgls_ctx* ctx, int curve, const uint8_t* partials, size_t k, uint8_t* out_gt, int* is_identity) {
+    if (!ctx || !curve_ok(curve) || !out_gt || (k && !partials)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), bi = align_up(k * 12 * F), bo = align_up(12 * F + 16);
+    int rc = ensure_scratch(ctx, bi + bo);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi;
+    int* dflag = (int*)(dout + 12 * F);
+    if (k) CU(cudaMemcpyAsync(din, partials, k * 12 * F, cudaMemcpyHostToDevice, ctx->stream));
+    rc = finish_bytes_dev(ctx, curve, din, k, 1, dout, dflag, ctx->stream);
+    if (rc) return rc;
+    uint8_t hbuf[12 * 48 + 16];
+    CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_gt, hbuf, 12 * F);
+    if (is_identity) memcpy(is_identity, hbuf + 12 * F, 4);
+    return BGLS_OK;
+}
+int bgls_gt_mul(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* b, uint8_t* out_gt) {
+    if (!ctx || !curve_ok(curve) || !a || !b || !out_gt) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), bi = align_up(2 * 12 * F), bo = align_up(12 * F + 16);
+    int rc = ensure_scratch(ctx, bi + bo);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi;
+    CU(cudaMemcpyAsync(din, a, 12 * F, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(din + 12 * F, b, 12 * F, cudaMemcpyHostToDevice, ctx->stream));
+    rc = finish_bytes_dev(ctx, curve, din, 2, 0, dout, nullptr, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_gt, dout, 12 * F, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BGLS_OK;
+}
+int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || !pts || !out || n == 0) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t rec = 2 * group * fp_bytes(curve), bi = align_up(n * rec), bo = align_up(rec);
+    const size_t bw = align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group));
+    int rc = ensure_scratch(ctx, bi + bo + bw);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi, *work = dout + bo;
+    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, ctx->stream));
+    rc = aggregate_dev(ctx, curve, group, din, n, dout, work, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BGLS_OK;
+}
+int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!pts || !scalars || !out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    if (n == 0) return BGLS_OK;
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t rec = 2 * group * fp_bytes(curve), bi = align_up(n * rec), bs = align_up(n * 32);
+    int rc = ensure_scratch(ctx, 2 * bi + bs);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)ctx->scratch, *dsc = din + bi, *dout = dsc + bs;
+    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dsc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    rc = scale_dev(ctx, curve, group, din, dsc, n, dout, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, dout, n * rec, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BGLS_OK;
+}
+int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, const uint64_t* offsets,
+                             size_t nbatch, uint8_t* out_ok) {
+    if (!ctx || !curve_ok(curve) || !offsets || (nbatch && !out_ok)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    if (nbatch == 0) return BGLS_OK;
+    for (size_t b = 0; b < nbatch; b++)
+        if (offsets[b + 1] < offsets[b]) return fail(ctx, BGLS_ERR_ARG, "offsets not monotone");
+    if (offsets[0] != 0) return fail(ctx, BGLS_ERR_ARG, "offsets[0] must be 0");
+    const size_t total = offsets[nbatch];
+    if (total && (!g1 || !g2)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), b1 = align_up(total * 2 * F), b2 = align_up(total * 4 * F);
+    const size_t bf = align_up((nbatch + 1) * 8), bk = align_up(nbatch), bw = align_up(total * fp12_dev_bytes(curve));
+    int rc = ensure_scratch(ctx, b1 + b2 + bf + bk + bw);
+    if (rc) return rc;
+    uint8_t *d1 = (uint8_t*)ctx->scratch, *d2 = d1 + b1, *doff = d2 + b2, *dok = doff + bf, *work = dok + bk;
+    if (total) {
+        CU(cudaMemcpyAsync(d1, g1, total * 2 * F, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d2, g2, total * 4 * F, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(doff, offsets, (nbatch + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = batch_dev(ctx, curve, d1, d2, doff, nbatch, total, dok, work, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_ok, dok, nbatch, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BGLS_OK;
+}
+
+// ---- device-resident entry points (no synchronisation)
+static int dev_work(bgls_ctx* ctx, size_t bytes, void** work) {
+    int rc = ensure_scratch(ctx, bytes);
+    if (rc) return rc;
+    *work = ctx->scratch;
+    return BGLS_OK;
+}
+int bgls_pairing_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, void* d_out_gt,
+                             void* d_is_identity, void* stream) {
+    if (!ctx || !curve_ok(curve) || !d_out_gt || (n && (!d_g1 || !d_g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    void* work;
+    int rc = dev_work(ctx, align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve)), &work);
+    if (rc) return rc;
+    return pairing_dev(ctx, curve, d_g1, d_g2, n, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
+}
+int bgls_miller_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, void* d_out_f, void* stream) {
+    if (!ctx || !curve_ok(curve) || !d_out_f || (n && (!d_g1 || !d_g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    void* work;
+    int rc = dev_work(ctx, align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve)), &work);
+    if (rc) return rc;
+    return pairing_dev(ctx, curve, d_g1, d_g2, n, 0, d_out_f, nullptr, work, (cudaStream_t)stream);
+}
+int bgls_final_exp_product_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, void* d_out_gt,
+                               void* d_is_identity, void* stream) {
+    if (!ctx || !curve_ok(curve) || !d_out_gt || (k && !d_partials)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    return finish_bytes_dev(ctx, curve, d_partials, k, 1, d_out_gt, d_is_identity, (cudaStream_t)stream);
+}
+int bgls_aggregate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* stream) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || !d_pts || !d_out || n == 0) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    void* work;
+    int rc = dev_work(ctx, align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group)), &work);
+    if (rc) return rc;
+    return aggregate_dev(ctx, curve, group, d_pts, n, d_out, work, (cudaStream_t)stream);
+}
+int bgls_scale_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void* d_scalars, size_t n,
+                          void* d_out, void* stream) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!d_pts || !d_scalars || !d_out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    return scale_dev(ctx, curve, group, d_pts, d_scalars, n, d_out, (cudaStream_t)stream);
+}
+int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_offsets,
+                                 size_t nbatch, size_t total_pairs, void* d_out_ok, void* stream) {
+    if (!ctx || !curve_ok(curve) || !d_offsets || (nbatch && !d_out_ok) || (total_pairs && (!d_g1 || !d_g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    void* work;
+    int rc = dev_work(ctx, align_up(total_pairs * fp12_dev_bytes(curve)), &work);
+    if (rc) return rc;
+    return batch_dev(ctx, curve, d_g1, d_g2, d_offsets, nbatch, total_pairs, d_out_ok, work, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+/* bgls_b200 -- C ABI of the B200 aggregate-signature verification engine.
+ *
+ * Drop-in boundary for the hot path of Project-Arda/bgls.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - curve ids: BGLS_ALTBN128 (reference singleton `Altbn128`, curves/altbn128.go:32) and
+ *     BGLS_BLS12_381 (`Bls12`, curves/bls12_381.go:31).
+ *   - points cross the boundary as the reference's *uncompressed affine big-endian* records,
+ *     i.e. exactly what Point.MarshalUncompressed() emits (curves/altbn128.go:91-93,223-225;
+ *     curves/bls12_381.go:61-63,122-124):
+ *         G1 = x || y                      (2 * F bytes)      F = 32 (altbn128), 48 (bls12-381)
+ *         G2 = x_im || x_re || y_im || y_re (4 * F bytes)
+ *         GT = 12 * F bytes, coefficients of w^5,w^3,w^1,w^4,w^2,w^0, each (im, re)
+ *              (the cloudflare bn256 gfP12 marshal order, curves/altbn128.go:378-380)
+ *     The point at infinity is the all-zero record (curves/README.md:19); for bls12-381 a record
+ *     whose first byte has bit 0x40 set is also accepted as infinity.  Outputs always use zeros.
+ *   - inputs must be on-curve, reduced (< p) coordinates: the reference rejects anything else when
+ *     the Point is constructed (curves/altbn128.go:50-55,172-177), before this boundary.
+ *     No subgroup check is made, as in the reference.
+ *   - every function returns BGLS_OK (0) or a negative error; the Go side maps non-zero to
+ *     `ok == false` / `nil` (curves/curve.go:126-128,137-139).  bgls_last_error() gives the text.
+ *   - host-buffer entry points copy in, run on the context's stream and synchronise before
+ *     returning.  `_dev` entry points take device pointers (16-byte aligned) and a cudaStream_t
+ *     (as void*), enqueue the work and return without synchronising.
+ *   - a context is bound to one CUDA device and is internally serialised (safe to share between
+ *     threads / goroutines; calls on one context do not run concurrently).
+ */
+#ifndef BGLS_B200_H
+#define BGLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGLS_ALTBN128 0
+#define BGLS_BLS12_381 1
+
+#define BGLS_G1 1
+#define BGLS_G2 2
+
+#define BGLS_OK 0
+#define BGLS_ERR_ARG (-1)   /* bad curve / group / null pointer */
+#define BGLS_ERR_CUDA (-2)  /* CUDA runtime error, see bgls_last_error */
+#define BGLS_ERR_NODEV (-3) /* no usable CUDA device: the engine has no CPU fallback */
+
+typedef struct bgls_ctx bgls_ctx;
+
+int bgls_ctx_create(int device, bgls_ctx** out);
+void bgls_ctx_destroy(bgls_ctx* ctx);
+const char* bgls_last_error(const bgls_ctx* ctx);
+/* library / kernel build identification, e.g. "bgls_b200 r1 sm_100a" */
+const char* bgls_version(void);
+
+/* CurveSystem.PairingProduct -- curves/curve.go:48,125-170; altbn128.go:143-145; bls12_381.go:238-240.
+ * out_gt = prod_i e(g1[i], g2[i]).  n == 0 yields the GT identity.  is_identity (may be NULL)
+ * receives PointT.Equals(GetGTIdentity()) (bgls/bgls.go:115-116). */
+int bgls_pairing_product(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n,
+                         uint8_t* out_gt, int* is_identity);
+
+/* CurveSystem.Pair -- curves/curve.go:46; altbn128.go:130-141; bls12_381.go:228-236. */
+int bgls_pair(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, uint8_t* out_gt);
+
+/* PointT.Add (GT multiplication) -- curves/altbn128.go:264-271; bls12_381.go:160-168. */
+int bgls_gt_mul(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* b, uint8_t* out_gt);
+
+/* AggregatePoints -- curves/curve.go:73-110 (also AggregateSignatures / AggregateKeys,
+ * bgls/bgls.go:123-131).  n >= 1; n == 0 returns BGLS_ERR_ARG (the reference never returns). */
+int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out);
+
+/* ScalePoints / Point.Mul -- curves/curve.go:190-214; altbn128.go:107-121,235-249.
+ * scalars: n records of 32 bytes, big-endian, non-negative. */
+int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, const uint8_t* scalars,
+                      size_t n, uint8_t* out);
+
+/* Signer-set sharding: product of the *Miller values* of n pairs without the
+ * final exponentiation (GT layout, 12*F bytes).  Partials from several GPUs are exchanged
+ * (e.g. NCCL all-gather) and finished with bgls_final_exp_product. */
+int bgls_miller_product(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out_f);
+int bgls_final_exp_product(bgls_ctx* ctx, int curve, const uint8_t* partials, size_t k, uint8_t* out_gt,
+                           int* is_identity);
+
+/* Throughput mode: nbatch independent pairing-product checks in one call.  Pairs of check b are
+ * [offsets[b], offsets[b+1]) in g1 / g2 (offsets has nbatch+1 entries).  out_ok[b] = 1 iff the
+ * product is the GT identity (one verifyAggSig each, bgls/bgls.go:94-119). */
+int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2,
+                             const uint64_t* offsets, size_t nbatch, uint8_t* out_ok);
+
+/* ---- device-resident variants: pointers are device memory, work is enqueued on `stream` ---- */
+/* d_out_gt: 12*F bytes; d_is_identity: one int32 (may be NULL) */
+int bgls_pairing_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n,
+                             void* d_out_gt, void* d_is_identity, void* stream);
+/* do_final = 0: raw Miller product (as bgls_miller_product) */
+int bgls_miller_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n,
+                            void* d_out_f, void* stream);
+int bgls_final_exp_product_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, void* d_out_gt,
+                               void* d_is_identity, void* stream);
+int bgls_aggregate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out,
+                              void* stream);
+int bgls_scale_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void* d_scalars,
+                          size_t n, void* d_out, void* stream);
+int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2,
+                                 const void* d_offsets, size_t nbatch, size_t total_pairs, void* d_out_ok,
+                                 void* stream);
+
+/* number of kernel launches issued through this context since creation (bench bookkeeping) */
+uint64_t bgls_launch_count(const bgls_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGLS_B200_H */

@@ -1,0 +1,184 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs (bit-exact) and against the committed golden vectors."""
+import random
+
+import pytest
+
+from oracle import c_oracle as C
+from tests.util import CURVES, GOLD, make_aggregate, rand_points, scalars_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import bgls_b200
+    c = bgls_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_golden_vectors(ctx, cid, c):
+    g = GOLD[c.name]
+    g1, g2, n = bytes.fromhex(g["g1"]), bytes.fromhex(g["g2"]), g["n"]
+    gt, one = ctx.pairing_product(cid, g1, g2, n)
+    assert gt.hex() == g["product_gt"] and not one
+    assert ctx.pair(cid, c.marshal_g1(c.g1), c.marshal_g2(c.g2)).hex() == g["gen_gt"]
+    nb = c.nbytes
+    assert ctx.pair(cid, g1[:2 * nb], g2[:4 * nb]).hex() == g["pair0_gt"]
+    assert ctx.aggregate_points(cid, 1, g1, n).hex() == g["sum_g1"]
+    assert ctx.aggregate_points(cid, 2, g2, n).hex() == g["sum_g2"]
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_golden_aggregate_signature(ctx, cid, c):
+    """bgls/bgls_test.go:40-77 shape on the golden 3-signer aggregate (real HashToG1 points)."""
+    a = GOLD[c.name]["agg"]
+    hs = [bytes.fromhex(h) for h in a["hashes"]]
+    pks = [bytes.fromhex(h) for h in a["pubkeys"]]
+    neg = c.marshal_g1(c.g1_neg(c.unmarshal_g1(bytes.fromhex(a["sig"]))))
+    g2gen = bytes.fromhex(a["g2gen"])
+    gt, ok = ctx.pairing_product(cid, b"".join(hs) + neg, b"".join(pks) + g2gen, 4)
+    assert ok and gt == c.marshal_gt(c.fp12_one)
+    # swapped messages, missing key, wrong signature -> reject
+    _, ok = ctx.pairing_product(cid, hs[1] + hs[0] + hs[2] + neg, b"".join(pks) + g2gen, 4)
+    assert not ok
+    _, ok = ctx.pairing_product(cid, hs[0] + hs[1] + neg, pks[0] + pks[1] + g2gen, 3)
+    assert not ok
+    bad = c.marshal_g1(c.g1_neg(c.g1_add(c.unmarshal_g1(bytes.fromhex(a["sig"])), c.g1)))
+    _, ok = ctx.pairing_product(cid, b"".join(hs) + bad, b"".join(pks) + g2gen, 4)
+    assert not ok
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 100])
+def test_pairing_product_random(ctx, cid, c, n):
+    """curves/curve_test.go:143-165 (TestPairingProd): product == prod of pairs, bit-exact GT bytes."""
+    rng = random.Random(1000 * cid + n)
+    g1, _ = rand_points(cid, c, 1, n, rng)
+    g2, _ = rand_points(cid, c, 2, n, rng)
+    gt, one = ctx.pairing_product(cid, g1, g2, n)
+    assert gt == C.pairing_product(cid, g1, g2, n, 8, 0)
+    assert not one
+    if n == 5:
+        # product of individually exponentiated pairings (the reference's structure)
+        assert gt == C.pairing_product(cid, g1, g2, n, 4, 1)
+        nb = c.nbytes
+        acc = c.marshal_gt(c.fp12_one)
+        for i in range(n):
+            acc = ctx.gt_mul(cid, acc, ctx.pair(cid, g1[2 * nb * i:2 * nb * (i + 1)], g2[4 * nb * i:4 * nb * (i + 1)]))
+        assert acc == gt
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_edge_cases(ctx, cid, c):
+    one = c.marshal_gt(c.fp12_one)
+    # n = 0: empty product is the identity
+    gt, ok = ctx.pairing_product(cid, b"", b"", 0)
+    assert gt == one and ok
+    # Pair with infinity is the identity (altbn128.go:478, bls12_381.go:341)
+    assert ctx.pair(cid, c.marshal_g1(None), c.marshal_g2(c.g2)) == one
+    assert ctx.pair(cid, c.marshal_g1(c.g1), c.marshal_g2(None)) == one
+    # infinity inside a product contributes nothing
+    rng = random.Random(9)
+    g1, _ = rand_points(cid, c, 1, 3, rng)
+    g2, _ = rand_points(cid, c, 2, 3, rng)
+    nb = c.nbytes
+    g1i = g1[:2 * nb] + c.marshal_g1(None) + g1[2 * nb:]
+    g2i = g2[:4 * nb] + c.marshal_g2(c.g2) + g2[4 * nb:]
+    assert ctx.pairing_product(cid, g1i, g2i, 4)[0] == ctx.pairing_product(cid, g1, g2, 3)[0]
+    # e(P,Q) * e(-P,Q) == 1
+    P = c.unmarshal_g1(g1[:2 * nb])
+    gt, ok = ctx.pairing_product(cid, g1[:2 * nb] + c.marshal_g1(c.g1_neg(P)), g2[:4 * nb] * 2, 2)
+    assert ok and gt == one
+    if cid == 1:  # bls12: 0x40 infinity flag accepted
+        flagged = bytes([0x40]) + bytes(2 * nb - 1)
+        assert ctx.pair(cid, flagged, c.marshal_g2(c.g2)) == one
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_sharded_miller_product(ctx, cid, c):
+    """per-shard Miller products, exchanged, multiplied, one final exponentiation."""
+    rng = random.Random(77 + cid)
+    n, shards = 37, 4
+    g1, _ = rand_points(cid, c, 1, n, rng)
+    g2, _ = rand_points(cid, c, 2, n, rng)
+    nb = c.nbytes
+    full, _ = ctx.pairing_product(cid, g1, g2, n)
+    parts = b""
+    for s in range(shards):
+        lo, hi = n * s // shards, n * (s + 1) // shards
+        parts += ctx.miller_product(cid, g1[2 * nb * lo:2 * nb * hi], g2[4 * nb * lo:4 * nb * hi], hi - lo)
+    gt, _ = ctx.final_exp_product(cid, parts, shards)
+    assert gt == full == C.pairing_product(cid, g1, g2, n, 8, 0)
+    # the raw Miller product itself is also bit-identical to the oracle's
+    assert ctx.miller_product(cid, g1, g2, n) == C.miller_product(cid, g1, g2, n, 4)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+@pytest.mark.parametrize("group", [1, 2])
+def test_aggregate_points(ctx, cid, c, group):
+    """curves/curve_test.go:167-186 (TestAggregation) + ragged sizes, infinity, repeats, cancellation."""
+    rng = random.Random(5 * cid + group)
+    rec = 2 * group * c.nbytes
+    for n in (1, 2, 3, 4, 6, 8, 31, 32, 33, 1000):
+        pts, ks = rand_points(cid, c, group, n, rng)
+        got = ctx.aggregate_points(cid, group, pts, n)
+        assert got == C.aggregate(cid, group, pts, n, 8), n
+        gen = c.marshal_g1(c.g1) if group == 1 else c.marshal_g2(c.g2)
+        assert got == C.scale_points(cid, group, gen, scalars_bytes([sum(ks) % c.r]), 1), n
+    pts, _ = rand_points(cid, c, group, 3, rng)
+    neg = c.marshal_g1(c.g1_neg(c.unmarshal_g1(pts[:rec]))) if group == 1 else c.marshal_g2(c.g2_neg(c.unmarshal_g2(pts[:rec])))
+    inf = bytes(rec)
+    mix = pts[:rec] + inf + pts[:rec] + pts[rec:2 * rec] + neg + inf + pts[2 * rec:]
+    assert ctx.aggregate_points(cid, group, mix, 7) == C.aggregate(cid, group, mix, 7, 1)
+    assert ctx.aggregate_points(cid, group, pts[:rec] + neg, 2) == inf
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+@pytest.mark.parametrize("group", [1, 2])
+def test_scale_points(ctx, cid, c, group):
+    """curves/curve_test.go:188-208 (TestScaling) and :120-141 (TestMul: k=0, 1, r-1)."""
+    rng = random.Random(50 * cid + group)
+    n = 40
+    pts, _ = rand_points(cid, c, group, n, rng)
+    ks = [0, 1, c.r - 1, c.r, 2] + [rng.randrange(c.r) for _ in range(n - 5)]
+    sc = scalars_bytes(ks)
+    assert ctx.scale_points(cid, group, pts, sc, n) == C.scale_points(cid, group, pts, sc, n, 8)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_batch_check(ctx, cid, c):
+    rng = random.Random(31 + cid)
+    sizes = [3, 1, 0, 5, 2]
+    g1 = g2 = b""
+    offsets = [0]
+    expect = []
+    nb = c.nbytes
+    for k, n in enumerate(sizes):
+        a1, a2 = make_aggregate(cid, c, n, rng)
+        good = (k % 2 == 0)
+        if not good:  # corrupt: replace the signature pair's G1 by the generator
+            a1 = a1[:-2 * nb] + c.marshal_g1(c.g1)
+        g1 += a1
+        g2 += a2
+        offsets.append(offsets[-1] + n + 1)
+        expect.append(good)
+    assert ctx.pairing_check_batch(cid, g1, g2, offsets) == expect
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_aggregate_verify_config_shape(ctx, cid, c):
+    """BASELINE config 2 shape (1024 signers -> 1025 pairs; 257 for bls12 to bound CPU time)."""
+    n = 1024 if cid == 0 else 256
+    rng = random.Random(2024 + cid)
+    g1, g2 = make_aggregate(cid, c, n, rng)
+    gt, ok = ctx.pairing_product(cid, g1, g2, n + 1)
+    assert ok and gt == c.marshal_gt(c.fp12_one)
+    assert gt == C.pairing_product(cid, g1, g2, n + 1, 8, 0)
+    # flip one hashed message -> reject, and GT bytes still match the oracle
+    nb = c.nbytes
+    bad = g1[2 * nb:4 * nb] + g1[2 * nb:]
+    gt, ok = ctx.pairing_product(cid, bad, g2, n + 1)
+    assert not ok and gt == C.pairing_product(cid, bad, g2, n + 1, 8, 0)
