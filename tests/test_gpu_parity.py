@@ -5,7 +5,7 @@ import random
 import pytest
 
 from oracle import c_oracle as C
-from tests.util import CURVES, GOLD, make_aggregate, rand_points, scalars_bytes
+from parity_util import CURVES, GOLD, make_aggregate, rand_points, scalars_bytes
 
 pytestmark = pytest.mark.gpu
 
