@@ -18,7 +18,7 @@ EXPORTS = [
     "bgls_ctx_create", "bgls_ctx_destroy", "bgls_last_error", "bgls_version", "bgls_pairing_product", "bgls_pair",
     "bgls_gt_mul", "bgls_aggregate_points", "bgls_scale_points", "bgls_miller_product", "bgls_final_exp_product",
     "bgls_pairing_check_batch", "bgls_pairing_product_dev", "bgls_miller_product_dev", "bgls_final_exp_product_dev",
-    "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count",
+    "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
 ]
 
 _lib = None
@@ -59,6 +59,9 @@ def load():
     L.bgls_pairing_check_batch_dev.argtypes = [vp, i, vp, vp, vp, sz, sz, vp, vp]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
+    L.bgls_set_profiling.argtypes = [vp, i]
+    L.bgls_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    L.bgls_intpipe_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
 
@@ -92,6 +95,23 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self._L.bgls_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        self._chk(self._L.bgls_set_profiling(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        self._chk(self._L.bgls_last_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def intpipe_peak(self) -> float:
+        v = ctypes.c_double(0)
+        self._chk(self._L.bgls_intpipe_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    def pairing_product_ptr(self, curve, h_g1: int, h_g2: int, n: int, h_out: int, h_flag: int):
+        """Host-buffer call on raw host addresses (e.g. pinned torch tensors)."""
+        self._chk(self._L.bgls_pairing_product(self._h, curve, h_g1, h_g2, n, h_out, ctypes.cast(h_flag, ctypes.POINTER(ctypes.c_int))))
 
     # ---- host-buffer API (bytes in / bytes out)
     def pairing_product(self, curve, g1: bytes, g2: bytes, n: int):

@@ -160,6 +160,22 @@ __global__ void __launch_bounds__(TB) k_scale(const uint8_t* __restrict__ pts, c
     jac_store<C>(out + i * rec, r);
 }
 
+// register-only full-rate IMAD.WIDE.U32 loop: the integer-pipe roofline denominator
+__global__ void k_intpipe_peak(uint32_t* out, uint32_t seed, int iters) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + 1;
+    unsigned long long w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = a * 7 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a), "r"(b));
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += w[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
+}
+
 }  // namespace bgls
 
 // ==================================================================== host side / C ABI
@@ -171,6 +187,8 @@ struct bgls_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     uint64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before main kernel, between, after finish
     std::mutex mu;
     std::string err;
 };
@@ -226,12 +244,15 @@ int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, siz
                     int* d_flag, void* work, cudaStream_t s) {
     const int nb = blocks_for(n);
     Fp12<C>* partial = (Fp12<C>*)work;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
     if (n > 0) {
         k_miller_product<C><<<nb, TB, 0, s>>>(d_g1, d_g2, n, partial);
         ctx->launches++;
     }
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
     k_finish<C, false><<<1, TB, 0, s>>>(partial, n > 0 ? (size_t)nb : 0, do_final, d_out, d_flag);
     ctx->launches++;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
     CU(cudaGetLastError());
     return BGLS_OK;
 }
@@ -334,10 +355,58 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < 3; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
 }
 const char* bgls_last_error(const bgls_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t bgls_launch_count(const bgls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bgls_set_profiling(bgls_ctx* ctx, int on) {
+    if (!ctx) return BGLS_ERR_ARG;
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0])
+        for (int i = 0; i < 3; i++) CU(cudaEventCreate(&ctx->ev[i]));
+    ctx->profiling = on != 0;
+    return BGLS_OK;
+}
+int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish) {
+    if (!ctx || !ctx->ev[0] || !ms_main || !ms_finish) return fail(ctx, BGLS_ERR_ARG, "profiling not enabled");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev[2]));
+    CU(cudaEventElapsedTime(ms_main, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(ms_finish, ctx->ev[1], ctx->ev[2]));
+    return BGLS_OK;
+}
+int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s) {
+    if (!ctx || !wide_mac_per_s) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 8192;
+    int rc = ensure_scratch(ctx, (size_t)blocks * threads * 4);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        k_intpipe_peak<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->scratch, 3, iters);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *wide_mac_per_s = (double)blocks * threads * iters * 8 / (best * 1e-3);
+    return BGLS_OK;
+}
 
 // ---- host-buffer entry points
 static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, int do_final,

@@ -106,8 +106,15 @@ int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, con
                                  const void* d_offsets, size_t nbatch, size_t total_pairs, void* d_out_ok,
                                  void* stream);
 
-/* number of kernel launches issued through this context since creation (bench bookkeeping) */
+/* ---- measurement helpers (bench.py); not part of the reference surface ---- */
+/* number of kernel launches issued through this context since creation */
 uint64_t bgls_launch_count(const bgls_ctx* ctx);
+/* when on, the pairing entry points bracket their kernels with CUDA events on the launching stream */
+int bgls_set_profiling(bgls_ctx* ctx, int on);
+/* device time of the last pairing call: Miller-loop kernel and finishing (product + final exp) kernel */
+int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish);
+/* measured full-rate IMAD.WIDE.U32 throughput of this GPU (32x32+64 multiply-accumulates / s) */
+int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s);
 
 #ifdef __cplusplus
 }
