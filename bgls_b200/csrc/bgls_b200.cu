@@ -10,12 +10,15 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 
 #include "../../include/bgls_b200.h"
 #include "pairing.cuh"
+#include "machine_kernels.cuh"
 
 namespace bgls {
 
@@ -181,7 +184,17 @@ __global__ void k_intpipe_peak(uint32_t* out, uint32_t seed, int iters) {
 // ==================================================================== host side / C ABI
 using namespace bgls;
 
+// device copies of the machine tables of one curve
+struct MachDev {
+    MachTables m{}, f{};
+    const uint16_t *miller = nullptr, *mul_ab = nullptr, *mul_ba = nullptr, *import_a = nullptr;
+    const uint16_t *finalexp = nullptr, *export_ = nullptr;
+    void* blob = nullptr;
+};
+
 struct bgls_ctx {
+    MachDev mach[2];
+    bool thread_engine = false;  // BGLS_ENGINE=thread selects the thread-per-pair reference kernels
     int device = 0;
     cudaStream_t stream = nullptr;
     void* scratch = nullptr;
@@ -268,12 +281,18 @@ int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, size_t rec,
 }
 
 int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
+                void* d_flag, void* work, cudaStream_t s);
+int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s);
+int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
+              void* d_ok, void* work, cudaStream_t s);
+
+int pairing_dev_thread(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
                 void* d_flag, void* work, cudaStream_t s) {
     if (curve == BGLS_ALTBN128)
         return enqueue_pairing<BN254>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
     return enqueue_pairing<BLS381>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
 }
-int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, cudaStream_t s) {
+int finish_bytes_dev_thread(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, cudaStream_t s) {
     if (curve == BGLS_ALTBN128) k_finish<BN254, true><<<1, TB, 0, s>>>(d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag);
     else k_finish<BLS381, true><<<1, TB, 0, s>>>(d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag);
     ctx->launches++;
@@ -308,7 +327,7 @@ int scale_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void
     CU(cudaGetLastError());
     return BGLS_OK;
 }
-int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
+int batch_dev_thread(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
               void* d_ok, void* work, cudaStream_t s) {
     const int nb1 = (int)((total + TB - 1) / TB), nb2 = (int)((nbatch + TB - 1) / TB);
     if (curve == BGLS_ALTBN128) {
@@ -321,6 +340,152 @@ int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, cons
     ctx->launches += (total ? 1 : 0) + (nbatch ? 1 : 0);
     CU(cudaGetLastError());
     return BGLS_OK;
+}
+
+// ---- machine tables upload
+template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, MachDev& d) {
+    struct Part { const void* src; size_t bytes; const void** dst; };
+    const Part parts[] = {
+        {MT::consts(), sizeof(uint32_t) * M::NCONST * M::L, (const void**)&d.m.consts},
+        {MT::hdr(), sizeof(uint32_t) * M::NPHASE, (const void**)&d.m.hdr},
+        {MT::rec(), sizeof(uint16_t) * M::NPHASE * MG * MREC, (const void**)&d.m.rec},
+        {FT::consts(), sizeof(uint32_t) * F::NCONST * F::L, (const void**)&d.f.consts},
+        {FT::hdr(), sizeof(uint32_t) * F::NPHASE, (const void**)&d.f.hdr},
+        {FT::rec(), sizeof(uint16_t) * F::NPHASE * MG * MREC, (const void**)&d.f.rec},
+        {MT::prog_MILLER(), sizeof(uint16_t) * M::MILLER_LEN, (const void**)&d.miller},
+        {MT::prog_MUL_AB(), sizeof(uint16_t) * M::MUL_AB_LEN, (const void**)&d.mul_ab},
+        {MT::prog_MUL_BA(), sizeof(uint16_t) * M::MUL_BA_LEN, (const void**)&d.mul_ba},
+        {MT::prog_IMPORT_A(), sizeof(uint16_t) * M::IMPORT_A_LEN, (const void**)&d.import_a},
+        {FT::prog_FINALEXP(), sizeof(uint16_t) * F::FINALEXP_LEN, (const void**)&d.finalexp},
+        {FT::prog_EXPORT(), sizeof(uint16_t) * F::EXPORT_LEN, (const void**)&d.export_},
+    };
+    size_t total = 0;
+    for (const Part& p : parts) total += align_up(p.bytes);
+    CU(cudaMalloc(&d.blob, total));
+    size_t off = 0;
+    for (const Part& p : parts) {
+        CU(cudaMemcpy((char*)d.blob + off, p.src, p.bytes, cudaMemcpyHostToDevice));
+        *p.dst = (char*)d.blob + off;
+        off += align_up(p.bytes);
+    }
+    CU(cudaFuncSetAttribute(k_mach_miller<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
+    CU(cudaFuncSetAttribute(k_mach_reduce<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
+    CU(cudaFuncSetAttribute(k_mach_import<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
+    CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(2)));
+    return BGLS_OK;
+}
+
+constexpr size_t MCHUNK = 8;  // fan-in of one product-tree level
+template <class M> size_t mach_val_bytes() { return (size_t)12 * M::L * sizeof(uint32_t); }
+template <class M> size_t mach_work_bytes(size_t n) { return align_up((n + 2) * mach_val_bytes<M>()) + align_up((n / MCHUNK + 3) * mach_val_bytes<M>()); }
+
+// product tree over `cnt` machine values in buf0 (scratch buf1); returns the buffer holding the single result
+template <class M>
+int mach_tree(bgls_ctx* ctx, const MachDev& d, uint32_t* buf0, uint32_t* buf1, size_t cnt, uint32_t** result, cudaStream_t s) {
+    uint32_t *cur = buf0, *oth = buf1;
+    if (cnt == 0) {  // empty product = 1
+        k_mach_reduce<M><<<1, MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, cur, 0, MCHUNK, nullptr, 1, oth);
+        ctx->launches++;
+        std::swap(cur, oth);
+        cnt = 1;
+    }
+    while (cnt > 1) {
+        const size_t nout = (cnt + MCHUNK - 1) / MCHUNK;
+        k_mach_reduce<M><<<(unsigned)((nout + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, cur, cnt, MCHUNK, nullptr, nout, oth);
+        ctx->launches++;
+        std::swap(cur, oth);
+        cnt = nout;
+    }
+    *result = cur;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+
+template <class M, class F>
+int mach_pairing(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final,
+                 uint8_t* d_out, int* d_flag, void* work, cudaStream_t s) {
+    uint32_t* buf0 = (uint32_t*)work;
+    uint32_t* buf1 = (uint32_t*)((char*)work + align_up((n + 2) * mach_val_bytes<M>()));
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
+    if (n > 0) {
+        k_mach_miller<M><<<(unsigned)((n + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, buf0);
+        ctx->launches++;
+    }
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
+    uint32_t* res;
+    int rc = mach_tree<M>(ctx, d, buf0, buf1, n, &res, s);
+    if (rc) return rc;
+    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(2), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
+                                                           res, 1, d_out, d_flag, nullptr);
+    ctx->launches++;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+// k partial products given as wire bytes -> product -> final exponentiation
+template <class M, class F>
+int mach_finish_bytes(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_partials, size_t k, int do_final, uint8_t* d_out, int* d_flag,
+                      void* work, cudaStream_t s) {
+    uint32_t* buf0 = (uint32_t*)work;
+    uint32_t* buf1 = (uint32_t*)((char*)work + align_up((k + 2) * mach_val_bytes<M>()));
+    if (k > 0) {
+        k_mach_import<M><<<(unsigned)((k + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.import_a, M::IMPORT_A_LEN, d_partials, k, buf0);
+        ctx->launches++;
+    }
+    uint32_t* res;
+    int rc = mach_tree<M>(ctx, d, buf0, buf1, k, &res, s);
+    if (rc) return rc;
+    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(2), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
+                                                           res, 1, d_out, d_flag, nullptr);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+// nbatch independent products (segments given by device offsets) -> identity flags
+template <class M, class F>
+int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8_t* d_g2, const unsigned long long* d_off, size_t nbatch,
+               size_t total, uint8_t* d_ok, void* work, cudaStream_t s) {
+    uint32_t* buf0 = (uint32_t*)work;
+    uint32_t* buf1 = (uint32_t*)((char*)work + align_up((total + 2) * mach_val_bytes<M>()));
+    if (total > 0) {
+        k_mach_miller<M><<<(unsigned)((total + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, total, buf0);
+        ctx->launches++;
+    }
+    k_mach_reduce<M><<<(unsigned)((nbatch + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, buf0, total, 0, d_off, nbatch, buf1);
+    k_mach_finish<F, M><<<(unsigned)((nbatch + 1) / 2), 32, mach_smem_bytes<F>(2), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+
+size_t mach_work_for(int curve, size_t n) {
+    return curve == BGLS_ALTBN128 ? mach_work_bytes<mtab::BN254_M>(n) : mach_work_bytes<mtab::BLS381_M>(n);
+}
+int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
+                void* d_flag, void* work, cudaStream_t s) {
+    if (ctx->thread_engine) return pairing_dev_thread(ctx, curve, d_g1, d_g2, n, do_final, d_out, d_flag, work, s);
+    if (curve == BGLS_ALTBN128)
+        return mach_pairing<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+    return mach_pairing<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+}
+int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s) {
+    if (ctx->thread_engine) return finish_bytes_dev_thread(ctx, curve, d_partials, k, do_final, d_out, d_flag, s);
+    if (curve == BGLS_ALTBN128)
+        return mach_finish_bytes<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+    return mach_finish_bytes<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+}
+int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
+              void* d_ok, void* work, cudaStream_t s) {
+    if (ctx->thread_engine) return batch_dev_thread(ctx, curve, d_g1, d_g2, d_off, nbatch, total, d_ok, work, s);
+    if (curve == BGLS_ALTBN128)
+        return mach_batch<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2, (const unsigned long long*)d_off, nbatch, total, (uint8_t*)d_ok, work, s);
+    return mach_batch<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2, (const unsigned long long*)d_off, nbatch, total, (uint8_t*)d_ok, work, s);
+}
+// scratch needed by the pairing pipelines for n pairs (either engine)
+size_t pairing_work_bytes(bgls_ctx* ctx, int curve, size_t n) {
+    const size_t t = align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
+    const size_t m = mach_work_for(curve, n);
+    return ctx->thread_engine ? t : (m > t ? m : t);
 }
 
 struct Guard {
@@ -346,6 +511,14 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
         delete ctx;
         return BGLS_ERR_CUDA;
     }
+    const char* eng = getenv("BGLS_ENGINE");
+    ctx->thread_engine = eng && std::string(eng) == "thread";
+    int rc = upload_mach<mtab::BN254_M, mtab::BN254_M_T, mtab::BN254_F, mtab::BN254_F_T>(ctx, ctx->mach[0]);
+    if (!rc) rc = upload_mach<mtab::BLS381_M, mtab::BLS381_M_T, mtab::BLS381_F, mtab::BLS381_F_T>(ctx, ctx->mach[1]);
+    if (rc) {
+        bgls_ctx_destroy(ctx);
+        return rc;
+    }
     *out = ctx;
     return BGLS_OK;
 }
@@ -354,6 +527,8 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto& d : ctx->mach)
+        if (d.blob) cudaFree(d.blob);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     for (int i = 0; i < 3; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -415,7 +590,7 @@ static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(n * 2 * F), b2 = align_up(n * 4 * F), bo = align_up(12 * F + 16);
-    const size_t bw = align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
+    const size_t bw = pairing_work_bytes(ctx, curve, n);
     int rc = ensure_scratch(ctx, b1 + b2 + bo + bw);
     if (rc) return rc;
     uint8_t* base = (uint8_t*)ctx->scratch;
@@ -448,12 +623,12 @@ int bgls_final_exp_product(bgls_ctx* ctx, int curve, const uint8_t* partials, si
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), bi = align_up(k * 12 * F), bo = align_up(12 * F + 16);
-    int rc = ensure_scratch(ctx, bi + bo);
+    int rc = ensure_scratch(ctx, bi + bo + mach_work_for(curve, k));
     if (rc) return rc;
     uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi;
     int* dflag = (int*)(dout + 12 * F);
     if (k) CU(cudaMemcpyAsync(din, partials, k * 12 * F, cudaMemcpyHostToDevice, ctx->stream));
-    rc = finish_bytes_dev(ctx, curve, din, k, 1, dout, dflag, ctx->stream);
+    rc = finish_bytes_dev(ctx, curve, din, k, 1, dout, dflag, dout + bo, ctx->stream);
     if (rc) return rc;
     uint8_t hbuf[12 * 48 + 16];
     CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -467,12 +642,12 @@ int bgls_gt_mul(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* b, ui
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), bi = align_up(2 * 12 * F), bo = align_up(12 * F + 16);
-    int rc = ensure_scratch(ctx, bi + bo);
+    int rc = ensure_scratch(ctx, bi + bo + mach_work_for(curve, 2));
     if (rc) return rc;
     uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi;
     CU(cudaMemcpyAsync(din, a, 12 * F, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(din + 12 * F, b, 12 * F, cudaMemcpyHostToDevice, ctx->stream));
-    rc = finish_bytes_dev(ctx, curve, din, 2, 0, dout, nullptr, ctx->stream);
+    rc = finish_bytes_dev(ctx, curve, din, 2, 0, dout, nullptr, dout + bo, ctx->stream);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_gt, dout, 12 * F, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -523,7 +698,8 @@ int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const 
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(total * 2 * F), b2 = align_up(total * 4 * F);
-    const size_t bf = align_up((nbatch + 1) * 8), bk = align_up(nbatch), bw = align_up(total * fp12_dev_bytes(curve));
+    const size_t bf = align_up((nbatch + 1) * 8), bk = align_up(nbatch);
+    const size_t bw = std::max(align_up(total * fp12_dev_bytes(curve)), mach_work_for(curve, total + nbatch));
     int rc = ensure_scratch(ctx, b1 + b2 + bf + bk + bw);
     if (rc) return rc;
     uint8_t *d1 = (uint8_t*)ctx->scratch, *d2 = d1 + b1, *doff = d2 + b2, *dok = doff + bf, *work = dok + bk;
@@ -552,7 +728,7 @@ int bgls_pairing_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const v
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve)), &work);
+    int rc = dev_work(ctx, pairing_work_bytes(ctx, curve, n), &work);
     if (rc) return rc;
     return pairing_dev(ctx, curve, d_g1, d_g2, n, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
 }
@@ -561,7 +737,7 @@ int bgls_miller_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const vo
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve)), &work);
+    int rc = dev_work(ctx, pairing_work_bytes(ctx, curve, n), &work);
     if (rc) return rc;
     return pairing_dev(ctx, curve, d_g1, d_g2, n, 0, d_out_f, nullptr, work, (cudaStream_t)stream);
 }
@@ -570,7 +746,10 @@ int bgls_final_exp_product_dev(bgls_ctx* ctx, int curve, const void* d_partials,
     if (!ctx || !curve_ok(curve) || !d_out_gt || (k && !d_partials)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
-    return finish_bytes_dev(ctx, curve, d_partials, k, 1, d_out_gt, d_is_identity, (cudaStream_t)stream);
+    void* work;
+    int rc = dev_work(ctx, mach_work_for(curve, k), &work);
+    if (rc) return rc;
+    return finish_bytes_dev(ctx, curve, d_partials, k, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
 }
 int bgls_aggregate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* stream) {
     if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || !d_pts || !d_out || n == 0) return fail(ctx, BGLS_ERR_ARG, "bad argument");
@@ -594,7 +773,7 @@ int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, con
     Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, align_up(total_pairs * fp12_dev_bytes(curve)), &work);
+    int rc = dev_work(ctx, std::max(align_up(total_pairs * fp12_dev_bytes(curve)), mach_work_for(curve, total_pairs + nbatch)), &work);
     if (rc) return rc;
     return batch_dev(ctx, curve, d_g1, d_g2, d_offsets, nbatch, total_pairs, d_out_ok, work, (cudaStream_t)stream);
 }

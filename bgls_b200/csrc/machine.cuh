@@ -1,0 +1,185 @@
+// Interpreter of the warp-cooperative "dot-product machine" (schedules: tools/gen_machine.py,
+// tables: machine_tables.cuh).
+//
+// A group of 16 lanes owns one pairing.  All state is a file of Fp slots in shared memory, stored
+// word-major (limb i of slot s at gs[i*NSG + s]) so that lanes reading different slots hit
+// different banks.  Fp elements are L limbs of 28 bits (unsaturated), Montgomery form with
+// R = 2^(28 L); values are only kept bounded (bounds proven statically by the generator).
+//   DOT task:  dst = MontRed( sum_t a_t * b_t )   -- products accumulate carry-free in 64-bit columns
+//              with full-rate IMAD.WIDE.U32 (measured 2x the throughput of the carry-chained form),
+//              one lazy reduction per output
+//   LIN task:  dst = Normalize( sum_t c_t * s_t  |  |c_t| * (KP - s_t) )
+// Host build (tests/host_emul) runs the same code sequentially over the lanes.
+#pragma once
+#include <cstdint>
+
+#include "arith.cuh"
+
+namespace bgls {
+
+constexpr int MG = 16;        // lanes per group
+constexpr int MREC = 26;      // u16 words per lane record
+constexpr uint32_t MIDLE = 0xFFFFu;
+
+template <class M> struct MachView {
+    uint32_t* gs;        // group slot file, word-major, NSG slots
+    const uint32_t* cs;  // block-shared constant slots, word-major, NCONST slots
+};
+
+template <class M> HD void mach_load(uint32_t* v, const MachView<M>& mv, uint32_t s) {
+    const bool isg = s < (uint32_t)M::NSG;
+    const uint32_t* base = isg ? mv.gs + s : mv.cs + (s - M::NSG);
+    const int stride = isg ? M::NSG : M::NCONST;
+#pragma unroll
+    for (int i = 0; i < M::L; i++) v[i] = base[i * stride];
+}
+template <class M> HD void mach_store(const MachView<M>& mv, uint32_t s, const uint32_t* v) {
+#pragma unroll
+    for (int i = 0; i < M::L; i++) mv.gs[i * M::NSG + s] = v[i];
+}
+
+// Montgomery reduction of 2L 64-bit columns (radix 2^W) to L normalised limbs: (T + m p) / R
+template <class M> HD void mach_montred(uint32_t* out, unsigned long long* acc) {
+    constexpr int L = M::L, W = M::W;
+    constexpr uint32_t MASK = (1u << W) - 1;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const uint32_t m = ((uint32_t)acc[i] * M::N0) & MASK;
+#pragma unroll
+        for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)m * M::p(j);
+        acc[i + 1] += acc[i] >> W;
+    }
+#pragma unroll
+    for (int k = L; k < 2 * L - 1; k++) {
+        acc[k + 1] += acc[k] >> W;
+        out[k - L] = (uint32_t)acc[k] & MASK;
+    }
+    out[L - 1] = (uint32_t)acc[2 * L - 1];
+}
+
+// one DOT task; rec: lane record, T: number of terms of the phase (uniform over the warp)
+template <class M> HD void mach_dot(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t* out) {
+    constexpr int L = M::L;
+    unsigned long long acc[2 * L];
+#pragma unroll
+    for (int i = 0; i < 2 * L; i++) acc[i] = 0;
+    for (int t = 0; t < T; t++) {
+        uint32_t a[L], b[L];
+        mach_load<M>(a, mv, rec[1 + t]);
+        mach_load<M>(b, mv, rec[13 + t]);
+#pragma unroll
+        for (int i = 0; i < L; i++)
+#pragma unroll
+            for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)a[i] * b[j];
+    }
+    mach_montred<M>(out, acc);
+}
+
+template <class M> HD void mach_lin(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t* out) {
+    constexpr int L = M::L, W = M::W;
+    constexpr uint32_t MASK = (1u << W) - 1;
+    unsigned long long acc[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) acc[i] = 0;
+    for (int t = 0; t < T; t++) {
+        const uint32_t cw = rec[13 + t];
+        const uint32_t c = cw & 0x7Fu;
+        const bool neg = (cw & 0x80u) != 0;
+        uint32_t v[L], k[L];
+        mach_load<M>(v, mv, rec[1 + t]);
+        mach_load<M>(k, mv, M::NSG + (cw >> 8));  // KP constant (slot 0 of the constants when unused)
+#pragma unroll
+        for (int i = 0; i < L; i++) {
+            const uint32_t x = neg ? k[i] - v[i] : v[i];
+            acc[i] += (unsigned long long)c * x;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < L - 1; i++) {
+        acc[i + 1] += acc[i] >> W;
+        out[i] = (uint32_t)acc[i] & MASK;
+    }
+    out[L - 1] = (uint32_t)acc[L - 1];
+}
+
+// big-endian field element (FP_BYTES) -> L raw limbs of W bits
+template <class M> HD void mach_limbs_from_be(uint32_t* out, const uint8_t* be) {
+    constexpr int NW = M::FP_BYTES / 4, L = M::L, W = M::W;
+    constexpr uint32_t MASK = (1u << W) - 1;
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const uint8_t* q = be + 4 * (NW - 1 - i);
+        w[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+    w[NW] = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const int bit = W * i, wi = bit >> 5, sh = bit & 31;
+        static_assert(W * (L - 1) / 32 < NW, "top limb must start inside the input words");
+        const uint32_t lo = w[wi], hi = w[wi + 1];  // w[NW] == 0
+        const uint32_t x = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+        out[i] = x & MASK;
+    }
+}
+// L limbs holding a value < 2p (plain domain) -> canonical big-endian bytes; returns true iff value == expect1 ? 1 : 0
+template <class M> HD void mach_canon_be(uint8_t* be, const uint32_t* limbs, bool* is_zero, bool* is_one) {
+    constexpr int NW = M::FP_BYTES / 4, L = M::L, W = M::W;
+    constexpr uint32_t MASK = (1u << W) - 1;
+    // conditional subtraction of p on W-bit limbs
+    uint32_t d[L];
+    int borrow = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        int x = (int)limbs[i] - (int)M::p(i) - borrow;
+        borrow = x < 0;
+        d[i] = (uint32_t)x & MASK;
+    }
+    uint32_t v[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) v[i] = borrow ? limbs[i] : d[i];
+    // repack to 32-bit words
+    uint32_t w[NW];
+    uint32_t nz = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const int bit = 32 * k, li = bit / W, sh = bit % W;
+        unsigned long long x = (unsigned long long)v[li] >> sh;
+        if (li + 1 < L) x |= (unsigned long long)v[li + 1] << (W - sh);
+        if (li + 2 < L && 2 * W - sh < 32) x |= (unsigned long long)v[li + 2] << (2 * W - sh);
+        w[k] = (uint32_t)x;
+        nz |= (k == 0) ? (w[k] ^ 1u) : w[k];
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        any |= w[k];
+        uint8_t* q = be + 4 * (NW - 1 - k);
+        q[0] = (uint8_t)(w[k] >> 24);
+        q[1] = (uint8_t)(w[k] >> 16);
+        q[2] = (uint8_t)(w[k] >> 8);
+        q[3] = (uint8_t)w[k];
+    }
+    *is_zero = any == 0;
+    *is_one = nz == 0;
+}
+
+// ---- tables on the device: one struct of pointers per slot file
+struct MachTables {
+    const uint32_t* consts;   // [NCONST][L]
+    const uint32_t* hdr;      // [NPHASE]
+    const uint16_t* rec;      // [NPHASE][16][26]
+};
+
+// run one phase for one lane (device) -- the caller synchronises the warp afterwards
+template <class M> HD void mach_phase_lane(const MachView<M>& mv, const MachTables& tb, uint32_t phase, int lane) {
+    const uint32_t h = tb.hdr[phase];
+    const int T = (h >> 8) & 0xFF;
+    const uint16_t* rec = tb.rec + ((size_t)phase * MG + lane) * MREC;
+    uint32_t out[M::L];
+    if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, T, out);
+    else mach_lin<M>(mv, rec, T, out);
+    if (rec[0] != MIDLE) mach_store<M>(mv, rec[0], out);
+}
+
+}  // namespace bgls

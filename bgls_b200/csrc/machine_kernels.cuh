@@ -1,0 +1,243 @@
+// Device kernels of the dot-product machine (see machine.cuh / tools/gen_machine.py).
+//   k_mach_miller    K1: one Miller loop per 16-lane group, two groups per warp
+//   k_mach_reduce    K2: Fp12 product tree (chunked or segmented), one group per output
+//   k_mach_finish    K3: final exponentiation (or plain export) + wire bytes + identity flag
+//   k_mach_import    wire bytes -> machine form (for bgls_final_exp_product)
+// Internal Fp12 values travel between kernels as [12][L] uint32 limbs (Montgomery, unsaturated).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "machine.cuh"
+#include "machine_tables.cuh"
+
+namespace bgls {
+
+constexpr int MWPB = 4;                 // warps per block
+constexpr int MGPB = MWPB * 2;          // groups per block
+
+template <class M> constexpr size_t mach_smem_bytes(int groups) {
+    return (size_t)(M::NCONST * M::L + groups * M::NSG * M::L) * sizeof(uint32_t);
+}
+
+template <class M> __device__ __forceinline__ void mach_load_consts(uint32_t* cs, const MachTables& tb) {
+    for (int idx = threadIdx.x; idx < M::NCONST * M::L; idx += blockDim.x) {
+        const int c = idx / M::L, i = idx % M::L;
+        cs[i * M::NCONST + c] = tb.consts[idx];
+    }
+    __syncthreads();
+}
+
+template <class M> __device__ __forceinline__ void mach_run(const MachView<M>& mv, const MachTables& tb,
+                                                            const uint16_t* __restrict__ prog, int len, int gl) {
+    for (int pc = 0; pc < len; pc++) {
+        const uint32_t ph = __ldg(prog + pc);
+        mach_phase_lane<M>(mv, tb, ph, gl);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- K1
+template <class M>
+__global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+                                                          const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                          size_t n, uint32_t* __restrict__ vals) {
+    extern __shared__ uint32_t sm[];
+    constexpr int L = M::L, FB = M::FP_BYTES;
+    uint32_t* cs = sm;
+    mach_load_consts<M>(cs, tb);
+    const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
+    const size_t pair = (size_t)blockIdx.x * MGPB + g;
+    const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
+    if (warp_first >= n) return;  // whole warp idle
+    MachView<M> mv;
+    mv.gs = sm + M::NCONST * L + (size_t)g * M::NSG * L;
+    mv.cs = cs;
+    const bool active = pair < n;
+    // inputs: lanes 0..5 of the group convert one coordinate each
+    bool zero = true, flag = false;
+    if (active && gl < 6) {
+        const uint8_t* src = gl < 2 ? g1 + pair * 2 * FB + gl * FB : g2 + pair * 4 * FB + (gl - 2) * FB;
+        const int slot = gl == 0 ? M::IN_XP : gl == 1 ? M::IN_YP : gl == 2 ? M::IN_XQY : gl == 3 ? M::IN_XQX : gl == 4 ? M::IN_YQY : M::IN_YQX;
+        uint32_t v[L];
+        mach_limbs_from_be<M>(v, src);
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < L; i++) any |= v[i];
+        zero = any == 0;
+        flag = FB == 48 && (gl == 0 || gl == 2) && (src[0] & 0x40);
+        mach_store<M>(mv, slot, v);
+    }
+    const unsigned zb = (__ballot_sync(0xFFFFFFFFu, zero) >> (threadIdx.x & 16)) & 0xFFFFu;
+    const unsigned fb = (__ballot_sync(0xFFFFFFFFu, flag) >> (threadIdx.x & 16)) & 0xFFFFu;
+    const bool inf = ((zb & 0x3u) == 0x3u) || ((zb & 0x3Cu) == 0x3Cu) || (fb & 0x5u);
+    __syncwarp();
+    mach_run<M>(mv, tb, prog, plen, gl);
+    if (active && gl < 12) {
+        uint32_t v[L];
+        mach_load<M>(v, mv, inf ? (gl == 0 ? M::ONE : M::ZERO) : M::FA0 + gl);
+        uint32_t* o = vals + (pair * 12 + gl) * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) o[i] = v[i];
+    }
+}
+
+// ---------------------------------------------------------------- K2
+// output g = product of inputs [lo, hi): lo/hi from `seg` (nout+1 offsets) when given, else chunks of `chunk`
+template <class M>
+__global__ void __launch_bounds__(MWPB * 32) k_mach_reduce(MachTables tb, const uint16_t* __restrict__ prog_ab,
+                                                          const uint16_t* __restrict__ prog_ba, const uint32_t* __restrict__ in,
+                                                          size_t n_in, size_t chunk, const unsigned long long* __restrict__ seg,
+                                                          size_t n_out, uint32_t* __restrict__ out) {
+    extern __shared__ uint32_t sm[];
+    constexpr int L = M::L;
+    uint32_t* cs = sm;
+    mach_load_consts<M>(cs, tb);
+    const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
+    const size_t o = (size_t)blockIdx.x * MGPB + g;
+    const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
+    if (warp_first >= n_out) return;
+    MachView<M> mv;
+    mv.gs = sm + M::NCONST * L + (size_t)g * M::NSG * L;
+    mv.cs = cs;
+    const bool active = o < n_out;
+    size_t lo = 0, hi = 0;
+    if (active) {
+        if (seg) { lo = seg[o]; hi = seg[o + 1]; }
+        else { lo = o * chunk; hi = lo + chunk < n_in ? lo + chunk : n_in; }
+    }
+    // the two groups of a warp walk in lock step: iterate to the longer of the two segments
+    const size_t len = hi - lo;
+    const size_t other = __shfl_xor_sync(0xFFFFFFFFu, (unsigned long long)len, 16);
+    const size_t steps = len > other ? len : other;
+    bool in_a = true;
+    if (gl < 12) {
+        uint32_t v[L];
+        if (len > 0) {
+            const uint32_t* src = in + (lo * 12 + gl) * L;
+#pragma unroll
+            for (int i = 0; i < L; i++) v[i] = src[i];
+        } else {
+            mach_load<M>(v, mv, gl == 0 ? M::ONE : M::ZERO);
+        }
+        mach_store<M>(mv, M::FA0 + gl, v);
+    }
+    __syncwarp();
+    for (size_t s = 1; s < steps; s++) {
+        if (gl < 12) {
+            uint32_t v[L];
+            if (s < len) {
+                const uint32_t* src = in + ((lo + s) * 12 + gl) * L;
+#pragma unroll
+                for (int i = 0; i < L; i++) v[i] = src[i];
+            } else {
+                mach_load<M>(v, mv, gl == 0 ? M::ONE : M::ZERO);  // multiply by one: keeps the warp uniform
+            }
+            mach_store<M>(mv, M::GB0 + gl, v);
+        }
+        __syncwarp();
+        mach_run<M>(mv, tb, in_a ? prog_ab : prog_ba, M::MUL_AB_LEN, gl);
+        in_a = !in_a;
+    }
+    if (active && gl < 12) {
+        uint32_t v[L];
+        mach_load<M>(v, mv, (in_a ? M::FA0 : M::FB0) + gl);
+        uint32_t* dst = out + (o * 12 + gl) * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) dst[i] = v[i];
+    }
+}
+
+// ---------------------------------------------------------------- K3
+// one group per value: FINALEXP (or EXPORT) then canonical wire bytes; flags[o] = 1 iff the result is 1
+template <class F, class MIN>
+__global__ void __launch_bounds__(32) k_mach_finish(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+                                                   const uint32_t* __restrict__ in, size_t n, uint8_t* __restrict__ out_gt,
+                                                   int* __restrict__ flags32, uint8_t* __restrict__ flags8) {
+    extern __shared__ uint32_t sm[];
+    constexpr int L = F::L, FB = F::FP_BYTES;
+    static_assert(F::L == MIN::L, "limb layout mismatch between slot files");
+    uint32_t* cs = sm;
+    mach_load_consts<F>(cs, tb);
+    const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
+    const size_t o = (size_t)blockIdx.x * 2 + g;
+    MachView<F> mv;
+    mv.gs = sm + F::NCONST * L + (size_t)g * F::NSG * L;
+    mv.cs = cs;
+    const bool active = o < n;
+    if (gl < 12) {
+        uint32_t v[L];
+        if (active) {
+            const uint32_t* src = in + (o * 12 + gl) * L;
+#pragma unroll
+            for (int i = 0; i < L; i++) v[i] = src[i];
+        } else {
+            mach_load<F>(v, mv, gl == 0 ? F::ONE : F::ZERO);
+        }
+        mach_store<F>(mv, F::FA0 + gl, v);
+    }
+    __syncwarp();
+    mach_run<F>(mv, tb, prog, plen, gl);
+    bool ok = true;
+    if (active && gl < 12) {
+        uint32_t v[L];
+        mach_load<F>(v, mv, F::OUT0 + gl);
+        const int k = gl >> 1, part = gl & 1;                       // coefficient of w^k, 0 = re, 1 = im
+        const int pos = k == 5 ? 0 : k == 3 ? 1 : k == 1 ? 2 : k == 4 ? 3 : k == 2 ? 4 : 5;  // GT order 5,3,1,4,2,0
+        bool z, one;
+        uint8_t bytes[FB];
+        mach_canon_be<F>(bytes, v, &z, &one);
+        if (out_gt) {
+            uint8_t* dst = out_gt + o * 12 * FB + (size_t)(2 * pos + (part ? 0 : 1)) * FB;
+#pragma unroll
+            for (int i = 0; i < FB; i++) dst[i] = bytes[i];
+        }
+        ok = (gl == 0) ? one : z;
+    }
+    const unsigned okb = (__ballot_sync(0xFFFFFFFFu, ok) >> (threadIdx.x & 16)) & 0xFFFFu;
+    if (active && gl == 0) {
+        const int is_one = (okb & 0xFFFu) == 0xFFFu;
+        if (flags32) flags32[o] = is_one;
+        if (flags8) flags8[o] = (uint8_t)is_one;
+    }
+}
+
+// ---------------------------------------------------------------- import: wire GT bytes -> machine form
+template <class M>
+__global__ void __launch_bounds__(MWPB * 32) k_mach_import(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+                                                          const uint8_t* __restrict__ in, size_t n, uint32_t* __restrict__ vals) {
+    extern __shared__ uint32_t sm[];
+    constexpr int L = M::L, FB = M::FP_BYTES;
+    uint32_t* cs = sm;
+    mach_load_consts<M>(cs, tb);
+    const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
+    const size_t o = (size_t)blockIdx.x * MGPB + g;
+    const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
+    if (warp_first >= n) return;
+    MachView<M> mv;
+    mv.gs = sm + M::NCONST * L + (size_t)g * M::NSG * L;
+    mv.cs = cs;
+    const bool active = o < n;
+    if (gl < 12) {
+        uint32_t v[L];
+        if (active) {
+            const int k = gl >> 1, part = gl & 1;
+            const int pos = k == 5 ? 0 : k == 3 ? 1 : k == 1 ? 2 : k == 4 ? 3 : k == 2 ? 4 : 5;
+            mach_limbs_from_be<M>(v, in + o * 12 * FB + (size_t)(2 * pos + (part ? 0 : 1)) * FB);
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; i++) v[i] = 0;
+        }
+        mach_store<M>(mv, M::RAWF0 + gl, v);
+    }
+    __syncwarp();
+    mach_run<M>(mv, tb, prog, plen, gl);
+    if (active && gl < 12) {
+        uint32_t v[L];
+        mach_load<M>(v, mv, M::FA0 + gl);
+        uint32_t* dst = vals + (o * 12 + gl) * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) dst[i] = v[i];
+    }
+}
+
+}  // namespace bgls

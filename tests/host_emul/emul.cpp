@@ -55,3 +55,113 @@ void emu_fpops(int curve, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     if (curve == 0) fpmul<BN254>(a, b, out); else fpmul<BLS381>(a, b, out);
 }
 }
+
+// ============================================================ dot-product machine (host emulation)
+#include <vector>
+#include "../../bgls_b200/csrc/machine.cuh"
+#include "../../bgls_b200/csrc/machine_tables.cuh"
+
+template <class M, class T> struct HostMach {
+    std::vector<uint32_t> gs, cs;
+    MachView<M> mv;
+    MachTables tb;
+    HostMach() : gs((size_t)M::NSG * M::L, 0), cs((size_t)M::NCONST * M::L, 0) {
+        for (int c = 0; c < M::NCONST; c++)
+            for (int i = 0; i < M::L; i++) cs[(size_t)i * M::NCONST + c] = T::consts()[c * M::L + i];
+        mv.gs = gs.data();
+        mv.cs = cs.data();
+        tb.consts = T::consts();
+        tb.hdr = T::hdr();
+        tb.rec = T::rec();
+    }
+    void run(const uint16_t* prog, int len) {
+        for (int pc = 0; pc < len; pc++) {
+            const uint32_t ph = prog[pc];
+            const uint32_t h = tb.hdr[ph];
+            const int Tn = (h >> 8) & 0xFF;
+            uint32_t outs[MG][M::L];
+            for (int lane = 0; lane < MG; lane++) {
+                const uint16_t* rec = tb.rec + ((size_t)ph * MG + lane) * MREC;
+                if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, Tn, outs[lane]);
+                else mach_lin<M>(mv, rec, Tn, outs[lane]);
+            }
+            for (int lane = 0; lane < MG; lane++) {  // deferred stores: a phase must be hazard-free
+                const uint16_t* rec = tb.rec + ((size_t)ph * MG + lane) * MREC;
+                if (rec[0] != MIDLE) mach_store<M>(mv, rec[0], outs[lane]);
+            }
+        }
+    }
+    void set(int s, const uint32_t* v) { mach_store<M>(mv, s, v); }
+    void get(int s, uint32_t* v) { mach_load<M>(v, mv, s); }
+};
+
+template <class MM, class MT, class FM, class FT>
+static int mach_pairing(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final, uint32_t* dbg_f) {
+    constexpr int L = MM::L, FB = MM::FP_BYTES;
+    HostMach<MM, MT> acc;   // accumulator group: product tree through MUL_AB / MUL_BA
+    bool have = false, in_a = true;
+    uint32_t one[L], zero[L];
+    acc.get(MM::ONE, one);
+    acc.get(MM::ZERO, zero);
+    for (size_t i = 0; i < n; i++) {
+        HostMach<MM, MT> m;
+        const uint8_t* p1 = g1 + i * 2 * FB;
+        const uint8_t* p2 = g2 + i * 4 * FB;
+        bool inf = bytes_all_zero(p1, 2 * FB) || bytes_all_zero(p2, 4 * FB) || (FB == 48 && ((p1[0] & 0x40) || (p2[0] & 0x40)));
+        uint32_t f[12][L];
+        if (inf) {
+            for (int k = 0; k < 12; k++) memcpy(f[k], k == 0 ? one : zero, sizeof(one));
+        } else {
+            uint32_t v[L];
+            mach_limbs_from_be<MM>(v, p1); m.set(MM::IN_XP, v);
+            mach_limbs_from_be<MM>(v, p1 + FB); m.set(MM::IN_YP, v);
+            mach_limbs_from_be<MM>(v, p2); m.set(MM::IN_XQY, v);
+            mach_limbs_from_be<MM>(v, p2 + FB); m.set(MM::IN_XQX, v);
+            mach_limbs_from_be<MM>(v, p2 + 2 * FB); m.set(MM::IN_YQY, v);
+            mach_limbs_from_be<MM>(v, p2 + 3 * FB); m.set(MM::IN_YQX, v);
+            m.run(MT::prog_MILLER(), MM::MILLER_LEN);
+            for (int k = 0; k < 12; k++) m.get(MM::FA0 + k, f[k]);
+        }
+        if (dbg_f && i == 0) memcpy(dbg_f, f, sizeof(f));
+        if (!have) {
+            for (int k = 0; k < 12; k++) acc.set(MM::FA0 + k, f[k]);
+            have = true; in_a = true;
+        } else {
+            for (int k = 0; k < 12; k++) acc.set(MM::GB0 + k, f[k]);
+            if (in_a) acc.run(MT::prog_MUL_AB(), MM::MUL_AB_LEN); else acc.run(MT::prog_MUL_BA(), MM::MUL_BA_LEN);
+            in_a = !in_a;
+        }
+    }
+    uint32_t f[12][L];
+    for (int k = 0; k < 12; k++) {
+        if (!have) memcpy(f[k], k == 0 ? one : zero, sizeof(one));
+        else acc.get((in_a ? MM::FA0 : MM::FB0) + k, f[k]);
+    }
+    HostMach<FM, FT> fe;
+    for (int k = 0; k < 12; k++) fe.set(FM::FA0 + k, f[k]);
+    if (do_final) {
+        fe.run(FT::prog_FINALEXP(), FM::FINALEXP_LEN);
+    } else {
+        fe.run(FT::prog_EXPORT(), FM::EXPORT_LEN);
+    }
+    // OUT slots: (k, re/im) -> GT layout: w-powers 5,3,1,4,2,0 each (im, re)
+    const int order[6] = {5, 3, 1, 4, 2, 0};
+    bool all_one = true;
+    for (int i = 0; i < 6; i++) {
+        for (int c = 0; c < 2; c++) {  // c = 0: im first
+            uint32_t v[L];
+            fe.get(FM::OUT0 + 2 * order[i] + (c == 0 ? 1 : 0), v);
+            bool z, o;
+            mach_canon_be<FM>(out + (2 * i + c) * FB, v, &z, &o);
+            const bool want_one = (order[i] == 0 && c == 1);
+            all_one = all_one && (want_one ? o : z);
+        }
+    }
+    return all_one ? 1 : 0;
+}
+
+extern "C" int emu_mach_pairing_product(int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final, uint32_t* dbg_f) {
+    using namespace mtab;
+    if (curve == 0) return mach_pairing<BN254_M, BN254_M_T, BN254_F, BN254_F_T>(g1, g2, n, out, do_final, dbg_f);
+    return mach_pairing<BLS381_M, BLS381_M_T, BLS381_F, BLS381_F_T>(g1, g2, n, out, do_final, dbg_f);
+}

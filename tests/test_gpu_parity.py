@@ -112,8 +112,9 @@ def test_sharded_miller_product(ctx, cid, c):
         parts += ctx.miller_product(cid, g1[2 * nb * lo:2 * nb * hi], g2[4 * nb * lo:4 * nb * hi], hi - lo)
     gt, _ = ctx.final_exp_product(cid, parts, shards)
     assert gt == full == C.pairing_product(cid, g1, g2, n, 8, 0)
-    # the raw Miller product itself is also bit-identical to the oracle's
-    assert ctx.miller_product(cid, g1, g2, n) == C.miller_product(cid, g1, g2, n, 4)
+    # the raw Miller product differs from the oracle's by subfield factors only (NAF loop, projective
+    # scalings): the oracle's final exponentiation of it must give the same GT element
+    assert C.fp12_product(cid, ctx.miller_product(cid, g1, g2, n), 1, True) == full
 
 
 @pytest.mark.parametrize("cid,c", CURVES)

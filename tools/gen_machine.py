@@ -897,6 +897,21 @@ def build_all(cfg):
     io["miller_in"], io["FA"] = build_miller(gm)
     _, io["FB"], io["GB"] = build_mulacc(gm)
     io["F_FA"], io["OUT"] = build_final_exp(gf)
+    p = cfg.p
+    # EXPORT (F file): OUT = FA out of Montgomery form, no exponentiation (raw Miller products for sharding)
+    gf.begin("EXPORT")
+    for k in range(6):
+        for c in range(2):
+            gf.set_ub(io["F_FA"][k][c], 64 * p)
+    gf.dot([(io["OUT"][k][c], [(io["F_FA"][k][c], gf.RAW1)]) for k in range(6) for c in range(2)])
+    # IMPORT_A / IMPORT_G (M file): plain-domain integers (wire bytes) -> Montgomery form in FA / GB
+    io["RAWF"] = gm.f12("RAWF")
+    for name, dst in (("IMPORT_A", io["FA"]), ("IMPORT_G", io["GB"])):
+        gm.begin(name)
+        for k in range(6):
+            for c in range(2):
+                gm.set_ub(io["RAWF"][k][c], p - 1)
+        gm.dot([(dst[k][c], [(io["RAWF"][k][c], gm.R2)]) for k in range(6) for c in range(2)])
     return {"M": gm, "F": gf}, io
 
 
@@ -922,11 +937,15 @@ def verify_all(cfg, gens, io):
     FFA, OUT = io["F_FA"], io["OUT"]
     rep["FINALEXP"], ubf = gf.verify_program("FINALEXP", {FFA[k][c]: 64 * p for k in range(6) for c in range(2)})
     assert max(ubf[OUT[k][c]] for k in range(6) for c in range(2)) < 2 * p, "final output must be < 2p for the epilogue"
+    rep["EXPORT"], ube = gf.verify_program("EXPORT", {FFA[k][c]: 64 * p for k in range(6) for c in range(2)})
+    assert max(ube[OUT[k][c]] for k in range(6) for c in range(2)) < 2 * p
+    for nm in ("IMPORT_A", "IMPORT_G"):
+        rep[nm], _ = gm.verify_program(nm, {io["RAWF"][k][c]: p - 1 for k in range(6) for c in range(2)})
     return {k: v.bit_length() for k, v in rep.items()}
 
 
 def emit_tables(path):
-    out = ["// GENERATED by tools/gen_machine.py -- do not edit.", "#pragma once", "#include <cstdint>", "namespace bgls {", "namespace mtab {"]
+    out = ["// GENERATED by tools/gen_machine.py -- do not edit.", "#pragma once", "#include <cstdint>", '#include "arith.cuh"', "namespace bgls {", "namespace mtab {"]
     for cfg in (BN, BLS):
         gens, io = build_all(cfg)
         bits = verify_all(cfg, gens, io)
@@ -940,13 +959,17 @@ def emit_tables(path):
             out.append("  static constexpr int W = %d, L = %d, NSG = %d, NCONST = %d, NPHASE = %d;" % (cfg.W, cfg.L, nsg, len(gen.cvals), len(gen.phases)))
             out.append("  static constexpr uint32_t N0 = 0x%xu;" % cfg.n0)
             out.append("  static constexpr int FP_BYTES = %d;" % (32 if cfg.name == "BN254" else 48))
+            out.append("  HD static constexpr uint32_t p(int i) {")
+            out.append("    constexpr uint32_t v[%d] = {%s};" % (cfg.L, ", ".join("0x%xu" % x for x in cfg.limbs(cfg.p))))
+            out.append("    return v[i];")
+            out.append("  }")
             for pname, prog in gen.programs.items():
                 out.append("  static constexpr int %s_LEN = %d;" % (pname, len(prog)))
             if tag == "M":
                 raw = io["miller_in"]
                 out.append("  static constexpr int IN_XP = %d, IN_YP = %d, IN_XQX = %d, IN_XQY = %d, IN_YQX = %d, IN_YQY = %d;" % tuple(
                     ref(raw[k]) for k in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")))
-                regs_ = (("FA", io["FA"]), ("FB", io["FB"]), ("GB", io["GB"]))
+                regs_ = (("FA", io["FA"]), ("FB", io["FB"]), ("GB", io["GB"]), ("RAWF", io["RAWF"]))
             else:
                 regs_ = (("FA", io["F_FA"]), ("OUT", io["OUT"]))
             for nm, reg in regs_:
@@ -991,6 +1014,13 @@ def emit_tables(path):
             out.append("};")
             for pname, prog in gen.programs.items():
                 out.append("static const uint16_t %s_PROG_%s[%d] = {%s};" % (n, pname, len(prog), ",".join(str(x) for x in prog)))
+            out.append("struct %s_T {  // host-side accessors of the tables above" % n)
+            out.append("  static const uint32_t* consts() { return &%s_CONST[0][0]; }" % n)
+            out.append("  static const uint32_t* hdr() { return %s_PHASE_HDR; }" % n)
+            out.append("  static const uint16_t* rec() { return %s_PHASE_REC; }" % n)
+            for pname in gen.programs:
+                out.append("  static const uint16_t* prog_%s() { return %s_PROG_%s; }" % (pname, n, pname))
+            out.append("};")
     out += ["}  // namespace mtab", "}  // namespace bgls", ""]
     with open(path, "w") as f:
         f.write("\n".join(out))
