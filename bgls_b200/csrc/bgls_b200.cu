@@ -368,7 +368,8 @@ template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, M
         *p.dst = (char*)d.blob + off;
         off += align_up(p.bytes);
     }
-    CU(cudaFuncSetAttribute(k_mach_miller<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
+    CU(cudaFuncSetAttribute(k_mach_miller<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
+    CU(cudaFuncSetAttribute(k_mach_miller<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MWPB)));
     CU(cudaFuncSetAttribute(k_mach_reduce<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_import<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(2)));
@@ -376,6 +377,18 @@ template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, M
 }
 
 constexpr size_t MCHUNK = 8;  // fan-in of one product-tree level
+constexpr size_t MSMALL = 0;  // GPW=1 threshold: measured slower on B200 (1.55 ms vs 1.19 ms at 1025 pairs: the IMAD pipe is
+                              // charged per warp instruction, so half-empty warps double the pipe work); kept for experiments
+
+template <class M>
+void launch_miller(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, uint32_t* vals, cudaStream_t s) {
+    if (n == 0) return;
+    if (n <= MSMALL)
+        k_mach_miller<M, 1><<<(unsigned)((n + MWPB - 1) / MWPB), MWPB * 32, mach_smem_bytes<M>(MWPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, vals);
+    else
+        k_mach_miller<M, 2><<<(unsigned)((n + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, vals);
+    ctx->launches++;
+}
 template <class M> size_t mach_val_bytes() { return (size_t)12 * M::L * sizeof(uint32_t); }
 template <class M> size_t mach_work_bytes(size_t n) { return align_up((n + 2) * mach_val_bytes<M>()) + align_up((n / MCHUNK + 3) * mach_val_bytes<M>()); }
 
@@ -407,10 +420,7 @@ int mach_pairing(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uin
     uint32_t* buf0 = (uint32_t*)work;
     uint32_t* buf1 = (uint32_t*)((char*)work + align_up((n + 2) * mach_val_bytes<M>()));
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
-    if (n > 0) {
-        k_mach_miller<M><<<(unsigned)((n + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, buf0);
-        ctx->launches++;
-    }
+    launch_miller<M>(ctx, d, d_g1, d_g2, n, buf0, s);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
     uint32_t* res;
     int rc = mach_tree<M>(ctx, d, buf0, buf1, n, &res, s);
@@ -447,10 +457,7 @@ int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8
                size_t total, uint8_t* d_ok, void* work, cudaStream_t s) {
     uint32_t* buf0 = (uint32_t*)work;
     uint32_t* buf1 = (uint32_t*)((char*)work + align_up((total + 2) * mach_val_bytes<M>()));
-    if (total > 0) {
-        k_mach_miller<M><<<(unsigned)((total + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, total, buf0);
-        ctx->launches++;
-    }
+    launch_miller<M>(ctx, d, d_g1, d_g2, total, buf0, s);
     k_mach_reduce<M><<<(unsigned)((nbatch + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, buf0, total, 0, d_off, nbatch, buf1);
     k_mach_finish<F, M><<<(unsigned)((nbatch + 1) / 2), 32, mach_smem_bytes<F>(2), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
     ctx->launches += 2;

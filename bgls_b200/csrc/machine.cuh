@@ -57,20 +57,27 @@ template <class M> HD void mach_montred(uint32_t* out, unsigned long long* acc) 
     out[L - 1] = (uint32_t)acc[2 * L - 1];
 }
 
-// one DOT task; rec: lane record, T: number of terms of the phase (uniform over the warp)
+// one DOT task; rec: lane record, T: number of terms of the phase (uniform over the warp).
+// The operands of term t+1 are fetched while the L*L multiply-accumulates of term t issue.
 template <class M> HD void mach_dot(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t* out) {
     constexpr int L = M::L;
     unsigned long long acc[2 * L];
 #pragma unroll
     for (int i = 0; i < 2 * L; i++) acc[i] = 0;
+    uint32_t a[L], b[L];
+    mach_load<M>(a, mv, rec[1]);
+    mach_load<M>(b, mv, rec[13]);
     for (int t = 0; t < T; t++) {
-        uint32_t a[L], b[L];
-        mach_load<M>(a, mv, rec[1 + t]);
-        mach_load<M>(b, mv, rec[13 + t]);
+        uint32_t na[L], nb[L];
+        const int tn = t + 1 < T ? t + 1 : t;
+        mach_load<M>(na, mv, rec[1 + tn]);
+        mach_load<M>(nb, mv, rec[13 + tn]);
 #pragma unroll
         for (int i = 0; i < L; i++)
 #pragma unroll
             for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)a[i] * b[j];
+#pragma unroll
+        for (int i = 0; i < L; i++) { a[i] = na[i]; b[i] = nb[i]; }
     }
     mach_montred<M>(out, acc);
 }

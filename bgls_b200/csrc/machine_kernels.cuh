@@ -15,43 +15,70 @@ namespace bgls {
 constexpr int MWPB = 4;                 // warps per block
 constexpr int MGPB = MWPB * 2;          // groups per block
 
+// shared memory layout of every machine kernel (32-bit words):
+//   [ constants (word-major) | phase headers | phase records (u16 x 26 x 16 per phase) | group slot files ]
+// Keeping the schedule tables on chip removes every global load from the phase loop.
+template <class M> __host__ __device__ constexpr size_t mach_tab_words() {
+    return (size_t)M::NCONST * M::L + M::NPHASE + ((size_t)M::NPHASE * MG * MREC + 1) / 2;
+}
 template <class M> constexpr size_t mach_smem_bytes(int groups) {
-    return (size_t)(M::NCONST * M::L + groups * M::NSG * M::L) * sizeof(uint32_t);
+    return (mach_tab_words<M>() + (size_t)groups * M::NSG * M::L) * sizeof(uint32_t);
 }
 
-template <class M> __device__ __forceinline__ void mach_load_consts(uint32_t* cs, const MachTables& tb) {
+// copies the tables into shared memory; returns the group area and rewrites `tb` to the on-chip copies
+template <class M> __device__ __forceinline__ uint32_t* mach_stage_tables(uint32_t* sm, MachTables& tb) {
+    uint32_t* cs = sm;
+    uint32_t* hdr = cs + M::NCONST * M::L;
+    uint32_t* rec = hdr + M::NPHASE;
     for (int idx = threadIdx.x; idx < M::NCONST * M::L; idx += blockDim.x) {
         const int c = idx / M::L, i = idx % M::L;
         cs[i * M::NCONST + c] = tb.consts[idx];
     }
+    for (int idx = threadIdx.x; idx < M::NPHASE; idx += blockDim.x) hdr[idx] = tb.hdr[idx];
+    const uint32_t* rsrc = (const uint32_t*)tb.rec;   // NPHASE*16*26 u16 = even number of u16
+    constexpr int RW = M::NPHASE * MG * MREC / 2;
+    for (int idx = threadIdx.x; idx < RW; idx += blockDim.x) rec[idx] = rsrc[idx];
     __syncthreads();
+    tb.consts = cs;
+    tb.hdr = hdr;
+    tb.rec = (const uint16_t*)rec;
+    return sm + mach_tab_words<M>();
 }
 
 template <class M> __device__ __forceinline__ void mach_run(const MachView<M>& mv, const MachTables& tb,
-                                                            const uint16_t* __restrict__ prog, int len, int gl) {
+                                                            const uint16_t* __restrict__ prog, int len, int gl,
+                                                            unsigned wmask = 0xFFFFFFFFu) {
+    uint32_t ph = __ldg(prog);
     for (int pc = 0; pc < len; pc++) {
-        const uint32_t ph = __ldg(prog + pc);
+        const uint32_t nxt = __ldg(prog + (pc + 1 < len ? pc + 1 : pc));  // prefetch: hides the global latency
         mach_phase_lane<M>(mv, tb, ph, gl);
-        __syncwarp();
+        __syncwarp(wmask);
+        ph = nxt;
     }
 }
 
 // ---------------------------------------------------------------- K1
-template <class M>
+// GPW = groups per warp.  GPW = 2 packs two pairings into each warp (throughput mode).  GPW = 1 leaves
+// lanes 16..31 idle but doubles the number of resident warps: one warp per SM sub-partition only
+// reaches about half of the IMAD.WIDE issue rate (ncu: issue active 27 %, stall_wait 2.2), so small
+// products (the 1025-pair aggregate verify) run faster with more, half-empty warps.
+template <class M, int GPW>
 __global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const uint16_t* __restrict__ prog, int plen,
                                                           const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                           size_t n, uint32_t* __restrict__ vals) {
     extern __shared__ uint32_t sm[];
     constexpr int L = M::L, FB = M::FP_BYTES;
-    uint32_t* cs = sm;
-    mach_load_consts<M>(cs, tb);
-    const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
-    const size_t pair = (size_t)blockIdx.x * MGPB + g;
-    const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
+    constexpr int GPB = MWPB * GPW;  // groups per block
+    uint32_t* gbase = mach_stage_tables<M>(sm, tb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (GPW == 1 && lane >= MG) return;
+    const int g = GPW == 2 ? (threadIdx.x >> 4) : warp, gl = lane & 15;
+    const size_t pair = (size_t)blockIdx.x * GPB + g;
+    const size_t warp_first = (size_t)blockIdx.x * GPB + (GPW == 2 ? (g & ~1) : g);
     if (warp_first >= n) return;  // whole warp idle
     MachView<M> mv;
-    mv.gs = sm + M::NCONST * L + (size_t)g * M::NSG * L;
-    mv.cs = cs;
+    mv.gs = gbase + (size_t)g * M::NSG * L;
+    mv.cs = tb.consts;
     const bool active = pair < n;
     // inputs: lanes 0..5 of the group convert one coordinate each
     bool zero = true, flag = false;
@@ -67,11 +94,12 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const 
         flag = FB == 48 && (gl == 0 || gl == 2) && (src[0] & 0x40);
         mach_store<M>(mv, slot, v);
     }
-    const unsigned zb = (__ballot_sync(0xFFFFFFFFu, zero) >> (threadIdx.x & 16)) & 0xFFFFu;
-    const unsigned fb = (__ballot_sync(0xFFFFFFFFu, flag) >> (threadIdx.x & 16)) & 0xFFFFu;
+    const unsigned wmask = GPW == 2 ? 0xFFFFFFFFu : 0xFFFFu;
+    const unsigned zb = (__ballot_sync(wmask, zero) >> (lane & 16)) & 0xFFFFu;
+    const unsigned fb = (__ballot_sync(wmask, flag) >> (lane & 16)) & 0xFFFFu;
     const bool inf = ((zb & 0x3u) == 0x3u) || ((zb & 0x3Cu) == 0x3Cu) || (fb & 0x5u);
-    __syncwarp();
-    mach_run<M>(mv, tb, prog, plen, gl);
+    __syncwarp(wmask);
+    mach_run<M>(mv, tb, prog, plen, gl, wmask);
     if (active && gl < 12) {
         uint32_t v[L];
         mach_load<M>(v, mv, inf ? (gl == 0 ? M::ONE : M::ZERO) : M::FA0 + gl);
@@ -90,15 +118,14 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_reduce(MachTables tb, const 
                                                           size_t n_out, uint32_t* __restrict__ out) {
     extern __shared__ uint32_t sm[];
     constexpr int L = M::L;
-    uint32_t* cs = sm;
-    mach_load_consts<M>(cs, tb);
+    uint32_t* gbase = mach_stage_tables<M>(sm, tb);
     const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
     const size_t o = (size_t)blockIdx.x * MGPB + g;
     const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
     if (warp_first >= n_out) return;
     MachView<M> mv;
-    mv.gs = sm + M::NCONST * L + (size_t)g * M::NSG * L;
-    mv.cs = cs;
+    mv.gs = gbase + (size_t)g * M::NSG * L;
+    mv.cs = tb.consts;
     const bool active = o < n_out;
     size_t lo = 0, hi = 0;
     if (active) {
@@ -156,13 +183,12 @@ __global__ void __launch_bounds__(32) k_mach_finish(MachTables tb, const uint16_
     extern __shared__ uint32_t sm[];
     constexpr int L = F::L, FB = F::FP_BYTES;
     static_assert(F::L == MIN::L, "limb layout mismatch between slot files");
-    uint32_t* cs = sm;
-    mach_load_consts<F>(cs, tb);
+    uint32_t* gbase = mach_stage_tables<F>(sm, tb);
     const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
     const size_t o = (size_t)blockIdx.x * 2 + g;
     MachView<F> mv;
-    mv.gs = sm + F::NCONST * L + (size_t)g * F::NSG * L;
-    mv.cs = cs;
+    mv.gs = gbase + (size_t)g * F::NSG * L;
+    mv.cs = tb.consts;
     const bool active = o < n;
     if (gl < 12) {
         uint32_t v[L];
@@ -207,15 +233,14 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_import(MachTables tb, const 
                                                           const uint8_t* __restrict__ in, size_t n, uint32_t* __restrict__ vals) {
     extern __shared__ uint32_t sm[];
     constexpr int L = M::L, FB = M::FP_BYTES;
-    uint32_t* cs = sm;
-    mach_load_consts<M>(cs, tb);
+    uint32_t* gbase = mach_stage_tables<M>(sm, tb);
     const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
     const size_t o = (size_t)blockIdx.x * MGPB + g;
     const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
     if (warp_first >= n) return;
     MachView<M> mv;
-    mv.gs = sm + M::NCONST * L + (size_t)g * M::NSG * L;
-    mv.cs = cs;
+    mv.gs = gbase + (size_t)g * M::NSG * L;
+    mv.cs = tb.consts;
     const bool active = o < n;
     if (gl < 12) {
         uint32_t v[L];
