@@ -1,0 +1,51 @@
+"""Signer-set sharding across GPUs: one process per GPU, `torch.distributed` for the
+plumbing.  Every rank multiplies the Miller values of its own contiguous slice of the packed
+(H(m_i), pk_i) arrays; the per-rank Fp12 partials (12*F bytes each) are all-gathered -- the only
+collective, pure latency over NVLink/NVSwitch -- and every rank finishes with one final
+exponentiation, so all ranks hold the verdict.  Point aggregation shards the same way with
+partial sums.
+
+`engine` is anything with the byte-level methods of bgls_b200.Context (miller_product,
+final_exp_product, aggregate_points): the CUDA context in production; the gloo CPU tests plug in
+the oracle to exercise exactly this orchestration without a GPU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ._native import FP_BYTES
+
+
+def _all_gather_bytes(blob: bytes, group=None, device=None) -> bytes:
+    world = dist.get_world_size(group)
+    t = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * len(blob), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return bytes(out.cpu().numpy().tobytes())
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous slice [lo, hi) of n items owned by `rank`."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def sharded_pairing_product(engine, curve: int, g1_local: bytes, g2_local: bytes, n_local: int, group=None, device=None):
+    """prod over all ranks' pairs of e(g1, g2): returns (gt_bytes, is_identity) on every rank."""
+    partial = engine.miller_product(curve, g1_local, g2_local, n_local)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return engine.final_exp_product(curve, partial, 1)
+    parts = _all_gather_bytes(partial, group, device)
+    return engine.final_exp_product(curve, parts, dist.get_world_size(group))
+
+
+def sharded_aggregate_points(engine, curve: int, grp: int, pts_local: bytes, n_local: int, group=None, device=None):
+    """sum over all ranks' points; a rank with an empty slice contributes the point at infinity."""
+    rec = 2 * grp * FP_BYTES[curve]
+    partial = engine.aggregate_points(curve, grp, pts_local, n_local) if n_local > 0 else bytes(rec)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return partial
+    parts = _all_gather_bytes(partial, group, device)
+    return engine.aggregate_points(curve, grp, parts, dist.get_world_size(group))

@@ -1,0 +1,96 @@
+"""The device arithmetic templates (bgls_b200/csrc/*.cuh) compiled for the host with emulated carry
+primitives (tests/host_emul/emul.cpp, test scaffolding) against the oracle: every algorithm the GPU
+runs -- saturated tower arithmetic, group law, and the dot-product machine interpreter with its
+generated programs -- is proven on a CPU-only machine."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import c_oracle as C
+from parity_util import CURVES, GOLD
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "host_emul")
+
+
+@pytest.fixture(scope="module")
+def E():
+    so = os.path.join(EMU, "libemul.so")
+    src = os.path.join(EMU, "emul.cpp")
+    csrc = os.path.join(os.path.dirname(HERE), "bgls_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
+    if not os.path.exists(so) or os.path.getmtime(so) < max(newest, os.path.getmtime(src)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    L = ctypes.CDLL(so)
+    u8p = ctypes.c_char_p
+    L.emu_pairing_product.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_size_t, u8p, ctypes.c_int]
+    L.emu_aggregate.argtypes = [ctypes.c_int, ctypes.c_int, u8p, ctypes.c_size_t, u8p]
+    L.emu_scale.argtypes = [ctypes.c_int, ctypes.c_int, u8p, u8p, ctypes.c_size_t, u8p]
+    L.emu_fpops.argtypes = [ctypes.c_int, u8p, u8p, u8p]
+    L.emu_mach_pairing_product.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_size_t, u8p, ctypes.c_int, ctypes.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_fp_ops_even_odd_montgomery(E, cid, c):
+    rng = random.Random(3)
+    nb = c.nbytes
+    cases = [(c.p - 1, c.p - 1), (0, 5), (1, 1)] + [(rng.randrange(c.p), rng.randrange(c.p)) for _ in range(200)]
+    for a, b in cases:
+        out = ctypes.create_string_buffer(4 * nb)
+        E.emu_fpops(cid, a.to_bytes(nb, "big"), b.to_bytes(nb, "big"), out)
+        o = out.raw
+        assert int.from_bytes(o[:nb], "big") == a * b % c.p
+        assert int.from_bytes(o[nb:2 * nb], "big") == (a + b) % c.p
+        assert int.from_bytes(o[2 * nb:3 * nb], "big") == (a - b) % c.p
+        if a:
+            assert int.from_bytes(o[3 * nb:], "big") == pow(a, -1, c.p)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_thread_engine_templates(E, cid, c):
+    g = GOLD[c.name]
+    g1, g2, n = bytes.fromhex(g["g1"]), bytes.fromhex(g["g2"]), g["n"]
+    nb = c.nbytes
+    out = ctypes.create_string_buffer(12 * nb)
+    E.emu_pairing_product(cid, g1, g2, n, out, 1)
+    assert out.raw.hex() == g["product_gt"]
+    E.emu_pairing_product(cid, g1, g2, n, out, 0)
+    assert out.raw == C.miller_product(cid, g1, g2, n)  # same formulas as the C oracle: raw values agree too
+    rng = random.Random(8)
+    for grp, key in ((1, "g1"), (2, "g2")):
+        blob = bytes.fromhex(g[key])
+        rec = 2 * grp * nb
+        o = ctypes.create_string_buffer(rec)
+        E.emu_aggregate(cid, grp, blob, n, o)
+        assert o.raw.hex() == g["sum_" + key]
+        sc = b"".join(rng.randrange(c.r).to_bytes(32, "big") for _ in range(n))
+        o = ctypes.create_string_buffer(rec * n)
+        E.emu_scale(cid, grp, blob, sc, n, o)
+        assert o.raw == C.scale_points(cid, grp, blob, sc, n)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_machine_interpreter_and_programs(E, cid, c):
+    g = GOLD[c.name]
+    g1, g2, n = bytes.fromhex(g["g1"]), bytes.fromhex(g["g2"]), g["n"]
+    nb = c.nbytes
+    out = ctypes.create_string_buffer(12 * nb)
+    assert E.emu_mach_pairing_product(cid, g1, g2, n, out, 1, None) == 0
+    assert out.raw.hex() == g["product_gt"]
+    # raw Miller product (EXPORT program): equal to the oracle's after the oracle's final exponentiation
+    E.emu_mach_pairing_product(cid, g1, g2, n, out, 0, None)
+    assert C.fp12_product(cid, out.raw, 1, True).hex() == g["product_gt"]
+    # valid aggregate signature + an infinity pair -> identity
+    a = g["agg"]
+    hs = [bytes.fromhex(h) for h in a["hashes"]]
+    pks = [bytes.fromhex(h) for h in a["pubkeys"]]
+    neg = c.marshal_g1(c.g1_neg(c.unmarshal_g1(bytes.fromhex(a["sig"]))))
+    G1 = b"".join(hs) + neg + c.marshal_g1(None)
+    G2 = b"".join(pks) + bytes.fromhex(a["g2gen"]) + c.marshal_g2(c.g2)
+    assert E.emu_mach_pairing_product(cid, G1, G2, 5, out, 1, None) == 1
+    assert out.raw == c.marshal_gt(c.fp12_one)
+    assert E.emu_mach_pairing_product(cid, b"", b"", 0, out, 1, None) == 1
