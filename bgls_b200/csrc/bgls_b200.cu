@@ -163,15 +163,20 @@ __global__ void __launch_bounds__(TB) k_scale(const uint8_t* __restrict__ pts, c
     jac_store<C>(out + i * rec, r);
 }
 
-// register-only full-rate IMAD.WIDE.U32 loop: the integer-pipe roofline denominator
+// register-only IMAD.WIDE.U32 loop: the integer-pipe roofline denominator.  The multiplier operand is
+// data dependent (low word of another accumulator), otherwise ptxas hoists the loop-invariant
+// product and the loop degenerates into 64-bit additions (which is what a first version measured).
 __global__ void k_intpipe_peak(uint32_t* out, uint32_t seed, int iters) {
-    uint32_t a = seed + threadIdx.x, b = seed * 3 + 1;
+    uint32_t b = seed * 3 + 1 + threadIdx.x;
     unsigned long long w[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) w[i] = a * 7 + i;
+    for (int i = 0; i < 8; i++) w[i] = (unsigned long long)(seed + threadIdx.x) * 7 + i;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a), "r"(b));
+        for (int i = 0; i < 8; i++) {
+            const uint32_t a = (uint32_t)w[(i + 4) & 7];  // depends on the accumulator updated four instructions ago
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a), "r"(b));
+        }
     }
     unsigned long long s = 0;
 #pragma unroll
@@ -194,7 +199,8 @@ struct MachDev {
 
 struct bgls_ctx {
     MachDev mach[2];
-    bool thread_engine = false;  // BGLS_ENGINE=thread selects the thread-per-pair reference kernels
+    bool thread_engine = false;  // BGLS_ENGINE=thread: thread-per-pair kernels only
+    bool machine_only = false;   // BGLS_ENGINE=machine: dot-product machine at every size (no hybrid)
     int device = 0;
     cudaStream_t stream = nullptr;
     void* scratch = nullptr;
@@ -348,10 +354,10 @@ template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, M
     const Part parts[] = {
         {MT::consts(), sizeof(uint32_t) * M::NCONST * M::L, (const void**)&d.m.consts},
         {MT::hdr(), sizeof(uint32_t) * M::NPHASE, (const void**)&d.m.hdr},
-        {MT::rec(), sizeof(uint16_t) * M::NPHASE * MG * MREC, (const void**)&d.m.rec},
+        {MT::rec(), sizeof(uint16_t) * M::NPHASE * M::LANES * M::REC, (const void**)&d.m.rec},
         {FT::consts(), sizeof(uint32_t) * F::NCONST * F::L, (const void**)&d.f.consts},
         {FT::hdr(), sizeof(uint32_t) * F::NPHASE, (const void**)&d.f.hdr},
-        {FT::rec(), sizeof(uint16_t) * F::NPHASE * MG * MREC, (const void**)&d.f.rec},
+        {FT::rec(), sizeof(uint16_t) * F::NPHASE * F::LANES * F::REC, (const void**)&d.f.rec},
         {MT::prog_MILLER(), sizeof(uint16_t) * M::MILLER_LEN, (const void**)&d.miller},
         {MT::prog_MUL_AB(), sizeof(uint16_t) * M::MUL_AB_LEN, (const void**)&d.mul_ab},
         {MT::prog_MUL_BA(), sizeof(uint16_t) * M::MUL_BA_LEN, (const void**)&d.mul_ba},
@@ -372,11 +378,12 @@ template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, M
     CU(cudaFuncSetAttribute(k_mach_miller<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MWPB)));
     CU(cudaFuncSetAttribute(k_mach_reduce<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_import<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
-    CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(2)));
+    CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(1)));
     return BGLS_OK;
 }
 
 constexpr size_t MCHUNK = 8;  // fan-in of one product-tree level
+constexpr size_t MHYBRID = 16384;  // pairs: above this the thread-per-pair Miller kernel wins (measured: 0.45 vs 0.65 us/pair)
 constexpr size_t MSMALL = 0;  // GPW=1 threshold: measured slower on B200 (1.55 ms vs 1.19 ms at 1025 pairs: the IMAD pipe is
                               // charged per warp instruction, so half-empty warps double the pipe work); kept for experiments
 
@@ -425,7 +432,7 @@ int mach_pairing(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uin
     uint32_t* res;
     int rc = mach_tree<M>(ctx, d, buf0, buf1, n, &res, s);
     if (rc) return rc;
-    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(2), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
+    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
                                                            res, 1, d_out, d_flag, nullptr);
     ctx->launches++;
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
@@ -445,7 +452,7 @@ int mach_finish_bytes(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_partials
     uint32_t* res;
     int rc = mach_tree<M>(ctx, d, buf0, buf1, k, &res, s);
     if (rc) return rc;
-    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(2), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
+    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
                                                            res, 1, d_out, d_flag, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -459,7 +466,7 @@ int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8
     uint32_t* buf1 = (uint32_t*)((char*)work + align_up((total + 2) * mach_val_bytes<M>()));
     launch_miller<M>(ctx, d, d_g1, d_g2, total, buf0, s);
     k_mach_reduce<M><<<(unsigned)((nbatch + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, buf0, total, 0, d_off, nbatch, buf1);
-    k_mach_finish<F, M><<<(unsigned)((nbatch + 1) / 2), 32, mach_smem_bytes<F>(2), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
+    k_mach_finish<F, M><<<(unsigned)nbatch, 32, mach_smem_bytes<F>(1), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
     ctx->launches += 2;
     CU(cudaGetLastError());
     return BGLS_OK;
@@ -471,6 +478,25 @@ size_t mach_work_for(int curve, size_t n) {
 int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
                 void* d_flag, void* work, cudaStream_t s) {
     if (ctx->thread_engine) return pairing_dev_thread(ctx, curve, d_g1, d_g2, n, do_final, d_out, d_flag, work, s);
+    if (n >= MHYBRID && !ctx->machine_only) {
+        // throughput regime: the thread-per-pair Miller kernel (Karatsuba towers, saturated limbs) does ~1.45x more
+        // pairs/s than the machine once the GPU is full; its raw product is handed to the machine for the
+        // latency-critical final exponentiation.  Layout of `work`: [thread partials | raw bytes | machine scratch]
+        const size_t F = fp_bytes(curve);
+        uint8_t* tw = (uint8_t*)work;
+        uint8_t* raw = tw + align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
+        uint8_t* mw = raw + align_up(12 * F);
+        if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
+        const bool prof = ctx->profiling;
+        ctx->profiling = false;
+        int rc = pairing_dev_thread(ctx, curve, d_g1, d_g2, n, 0, raw, nullptr, tw, s);
+        ctx->profiling = prof;
+        if (rc) return rc;
+        if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
+        rc = finish_bytes_dev(ctx, curve, raw, 1, do_final, d_out, d_flag, mw, s);
+        if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
+        return rc;
+    }
     if (curve == BGLS_ALTBN128)
         return mach_pairing<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
     return mach_pairing<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
@@ -492,7 +518,9 @@ int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, cons
 size_t pairing_work_bytes(bgls_ctx* ctx, int curve, size_t n) {
     const size_t t = align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
     const size_t m = mach_work_for(curve, n);
-    return ctx->thread_engine ? t : (m > t ? m : t);
+    if (ctx->thread_engine) return t;
+    if (n >= MHYBRID && !ctx->machine_only) return t + align_up(12 * fp_bytes(curve)) + mach_work_for(curve, 1);
+    return m > t ? m : t;
 }
 
 struct Guard {
@@ -520,6 +548,7 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     }
     const char* eng = getenv("BGLS_ENGINE");
     ctx->thread_engine = eng && std::string(eng) == "thread";
+    ctx->machine_only = eng && std::string(eng) == "machine";
     int rc = upload_mach<mtab::BN254_M, mtab::BN254_M_T, mtab::BN254_F, mtab::BN254_F_T>(ctx, ctx->mach[0]);
     if (!rc) rc = upload_mach<mtab::BLS381_M, mtab::BLS381_M_T, mtab::BLS381_F, mtab::BLS381_F_T>(ctx, ctx->mach[1]);
     if (rc) {

@@ -17,9 +17,10 @@
 
 namespace bgls {
 
-constexpr int MG = 16;        // lanes per group
-constexpr int MREC = 26;      // u16 words per lane record
+constexpr int MG = 16;        // lanes per group of the Miller / product slot files (two groups per warp)
 constexpr uint32_t MIDLE = 0xFFFFu;
+// per slot file (generated struct M): LANES lanes per group, lane record = REC u16:
+//   [0] dst, [1..TM] a slots (LIN: sources), [1+TM..2TM] b slots (LIN: coefficient words)
 
 template <class M> struct MachView {
     uint32_t* gs;        // group slot file, word-major, NSG slots
@@ -66,12 +67,12 @@ template <class M> HD void mach_dot(const MachView<M>& mv, const uint16_t* rec, 
     for (int i = 0; i < 2 * L; i++) acc[i] = 0;
     uint32_t a[L], b[L];
     mach_load<M>(a, mv, rec[1]);
-    mach_load<M>(b, mv, rec[13]);
+    mach_load<M>(b, mv, rec[1 + M::TM]);
     for (int t = 0; t < T; t++) {
         uint32_t na[L], nb[L];
         const int tn = t + 1 < T ? t + 1 : t;
         mach_load<M>(na, mv, rec[1 + tn]);
-        mach_load<M>(nb, mv, rec[13 + tn]);
+        mach_load<M>(nb, mv, rec[1 + M::TM + tn]);
 #pragma unroll
         for (int i = 0; i < L; i++)
 #pragma unroll
@@ -89,7 +90,7 @@ template <class M> HD void mach_lin(const MachView<M>& mv, const uint16_t* rec, 
 #pragma unroll
     for (int i = 0; i < L; i++) acc[i] = 0;
     for (int t = 0; t < T; t++) {
-        const uint32_t cw = rec[13 + t];
+        const uint32_t cw = rec[1 + M::TM + t];
         const uint32_t c = cw & 0x7Fu;
         const bool neg = (cw & 0x80u) != 0;
         uint32_t v[L], k[L];
@@ -175,14 +176,14 @@ template <class M> HD void mach_canon_be(uint8_t* be, const uint32_t* limbs, boo
 struct MachTables {
     const uint32_t* consts;   // [NCONST][L]
     const uint32_t* hdr;      // [NPHASE]
-    const uint16_t* rec;      // [NPHASE][16][26]
+    const uint16_t* rec;      // [NPHASE][LANES][REC]
 };
 
 // run one phase for one lane (device) -- the caller synchronises the warp afterwards
 template <class M> HD void mach_phase_lane(const MachView<M>& mv, const MachTables& tb, uint32_t phase, int lane) {
     const uint32_t h = tb.hdr[phase];
     const int T = (h >> 8) & 0xFF;
-    const uint16_t* rec = tb.rec + ((size_t)phase * MG + lane) * MREC;
+    const uint16_t* rec = tb.rec + ((size_t)phase * M::LANES + lane) * M::REC;
     uint32_t out[M::L];
     if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, T, out);
     else mach_lin<M>(mv, rec, T, out);

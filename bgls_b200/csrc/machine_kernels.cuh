@@ -19,7 +19,7 @@ constexpr int MGPB = MWPB * 2;          // groups per block
 //   [ constants (word-major) | phase headers | phase records (u16 x 26 x 16 per phase) | group slot files ]
 // Keeping the schedule tables on chip removes every global load from the phase loop.
 template <class M> __host__ __device__ constexpr size_t mach_tab_words() {
-    return (size_t)M::NCONST * M::L + M::NPHASE + ((size_t)M::NPHASE * MG * MREC + 1) / 2;
+    return (size_t)M::NCONST * M::L + M::NPHASE + ((size_t)M::NPHASE * M::LANES * M::REC + 1) / 2;
 }
 template <class M> constexpr size_t mach_smem_bytes(int groups) {
     return (mach_tab_words<M>() + (size_t)groups * M::NSG * M::L) * sizeof(uint32_t);
@@ -36,7 +36,7 @@ template <class M> __device__ __forceinline__ uint32_t* mach_stage_tables(uint32
     }
     for (int idx = threadIdx.x; idx < M::NPHASE; idx += blockDim.x) hdr[idx] = tb.hdr[idx];
     const uint32_t* rsrc = (const uint32_t*)tb.rec;   // NPHASE*16*26 u16 = even number of u16
-    constexpr int RW = M::NPHASE * MG * MREC / 2;
+    constexpr int RW = M::NPHASE * M::LANES * M::REC / 2;
     for (int idx = threadIdx.x; idx < RW; idx += blockDim.x) rec[idx] = rsrc[idx];
     __syncthreads();
     tb.consts = cs;
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_reduce(MachTables tb, const 
 }
 
 // ---------------------------------------------------------------- K3
-// one group per value: FINALEXP (or EXPORT) then canonical wire bytes; flags[o] = 1 iff the result is 1
+// one 32-lane group (one warp, one block) per value: FINALEXP (or EXPORT) then canonical wire bytes;
+// flags[o] = 1 iff the result is 1.  The F slot file splits every long dot over two lanes.
 template <class F, class MIN>
 __global__ void __launch_bounds__(32) k_mach_finish(MachTables tb, const uint16_t* __restrict__ prog, int plen,
                                                    const uint32_t* __restrict__ in, size_t n, uint8_t* __restrict__ out_gt,
@@ -183,28 +184,24 @@ __global__ void __launch_bounds__(32) k_mach_finish(MachTables tb, const uint16_
     extern __shared__ uint32_t sm[];
     constexpr int L = F::L, FB = F::FP_BYTES;
     static_assert(F::L == MIN::L, "limb layout mismatch between slot files");
+    static_assert(F::LANES == 32, "the final-exponentiation slot file is scheduled for 32-lane groups");
     uint32_t* gbase = mach_stage_tables<F>(sm, tb);
-    const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
-    const size_t o = (size_t)blockIdx.x * 2 + g;
+    const int gl = threadIdx.x;
+    const size_t o = blockIdx.x;
     MachView<F> mv;
-    mv.gs = gbase + (size_t)g * F::NSG * L;
+    mv.gs = gbase;
     mv.cs = tb.consts;
-    const bool active = o < n;
     if (gl < 12) {
         uint32_t v[L];
-        if (active) {
-            const uint32_t* src = in + (o * 12 + gl) * L;
+        const uint32_t* src = in + (o * 12 + gl) * L;
 #pragma unroll
-            for (int i = 0; i < L; i++) v[i] = src[i];
-        } else {
-            mach_load<F>(v, mv, gl == 0 ? F::ONE : F::ZERO);
-        }
+        for (int i = 0; i < L; i++) v[i] = src[i];
         mach_store<F>(mv, F::FA0 + gl, v);
     }
     __syncwarp();
     mach_run<F>(mv, tb, prog, plen, gl);
     bool ok = true;
-    if (active && gl < 12) {
+    if (gl < 12) {
         uint32_t v[L];
         mach_load<F>(v, mv, F::OUT0 + gl);
         const int k = gl >> 1, part = gl & 1;                       // coefficient of w^k, 0 = re, 1 = im
@@ -219,8 +216,8 @@ __global__ void __launch_bounds__(32) k_mach_finish(MachTables tb, const uint16_
         }
         ok = (gl == 0) ? one : z;
     }
-    const unsigned okb = (__ballot_sync(0xFFFFFFFFu, ok) >> (threadIdx.x & 16)) & 0xFFFFu;
-    if (active && gl == 0) {
+    const unsigned okb = __ballot_sync(0xFFFFFFFFu, ok);
+    if (gl == 0) {
         const int is_one = (okb & 0xFFFu) == 0xFFFu;
         if (flags32) flags32[o] = is_one;
         if (flags8) flags8[o] = (uint8_t)is_one;

@@ -79,14 +79,14 @@ template <class M, class T> struct HostMach {
             const uint32_t ph = prog[pc];
             const uint32_t h = tb.hdr[ph];
             const int Tn = (h >> 8) & 0xFF;
-            uint32_t outs[MG][M::L];
-            for (int lane = 0; lane < MG; lane++) {
-                const uint16_t* rec = tb.rec + ((size_t)ph * MG + lane) * MREC;
+            uint32_t outs[M::LANES][M::L];
+            for (int lane = 0; lane < M::LANES; lane++) {
+                const uint16_t* rec = tb.rec + ((size_t)ph * M::LANES + lane) * M::REC;
                 if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, Tn, outs[lane]);
                 else mach_lin<M>(mv, rec, Tn, outs[lane]);
             }
-            for (int lane = 0; lane < MG; lane++) {  // deferred stores: a phase must be hazard-free
-                const uint16_t* rec = tb.rec + ((size_t)ph * MG + lane) * MREC;
+            for (int lane = 0; lane < M::LANES; lane++) {  // deferred stores: a phase must be hazard-free
+                const uint16_t* rec = tb.rec + ((size_t)ph * M::LANES + lane) * M::REC;
                 if (rec[0] != MIDLE) mach_store<M>(mv, rec[0], outs[lane]);
             }
         }

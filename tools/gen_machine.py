@@ -110,9 +110,11 @@ class Phase:
 class Gen:
     """Builds phases/programs for one curve and tracks static value bounds."""
 
-    def __init__(self, cfg: Cfg):
+    def __init__(self, cfg: Cfg, lanes=G, tm=MAXT, split=False):
         self.cfg = cfg
+        self.lanes, self.tm, self.split = lanes, tm, split   # lanes per group, max terms per DOT record, split long dots
         self.gslots = {}       # name -> index (per-group slot)
+        self._nslots, self._pool, self._pools, self._pool_used = 0, None, {}, {}
         self.cslots = {}       # name -> index (block-shared constant slot)
         self.cvals = []        # constant limb vectors
         self.cints = []        # constant integer values (for the simulator)
@@ -140,8 +142,33 @@ class Gen:
     # ---- slots
     def g(self, name):
         if name not in self.gslots:
-            self.gslots[name] = len(self.gslots)
+            if self._pool is not None:
+                # temporaries of code regions that are never live at the same time share physical slots:
+                # the k-th new name of each region maps to the k-th slot of the pool
+                pool, ns = self._pool
+                k = self._pool_used.get((pool, ns), 0)
+                self._pool_used[(pool, ns)] = k + 1
+                slots = self._pools.setdefault(pool, [])
+                if k == len(slots):
+                    slots.append(self._nslots)
+                    self._nslots += 1
+                self.gslots[name] = slots[k]
+            else:
+                self.gslots[name] = self._nslots
+                self._nslots += 1
         return ("g", self.gslots[name])
+
+    def pool(self, pool, ns):
+        gen = self
+
+        class _P:
+            def __enter__(self_):
+                self_.prev = gen._pool
+                gen._pool = (pool, ns)
+
+            def __exit__(self_, *a):
+                gen._pool = self_.prev
+        return _P()
 
     def fp2(self, name):
         return (self.g(name + ".x"), self.g(name + ".y"))
@@ -170,7 +197,7 @@ class Gen:
     def emit(self, phase: Phase, key=None):
         """Append the phase to the current program (re-using an identical earlier phase)."""
         cfg = self.cfg
-        assert 0 < len(phase.tasks) and (phase.kind == "LIN" or len(phase.tasks) <= G), len(phase.tasks)
+        assert 0 < len(phase.tasks) <= self.lanes, len(phase.tasks)
         dsts = [t[0] for t in phase.tasks]
         assert len(set(dsts)) == len(dsts), "two tasks write one slot"
         reads = set()
@@ -182,7 +209,7 @@ class Gen:
                     reads.add(t[1])
         if phase.kind == "DOT":
             assert not (reads & set(dsts)), "DOT phase reads a slot it writes"
-            assert phase.T <= MAXT
+            assert phase.T <= self.tm
         else:
             # a LIN task may overwrite its own inputs (it reads everything before writing) but not
             # another task's inputs
@@ -262,19 +289,36 @@ class Gen:
 
     def lin_rounds(self, tasks):
         """LIN tasks, 16 per phase (a later round must not read what an earlier round wrote)."""
-        for i in range(G, len(tasks), G):
+        n = self.lanes
+        for i in range(n, len(tasks), n):
             written = {t[0] for t in tasks[:i]}
-            for d, terms in tasks[i:i + G]:
+            for d, terms in tasks[i:i + n]:
                 assert not ({t[0] for t in terms} & (written - {d})), "LIN rounds: read after write across rounds"
-        for i in range(0, len(tasks), G):
+        for i in range(0, len(tasks), n):
             ph = Phase("LIN")
-            ph.tasks = tasks[i:i + G]
+            ph.tasks = tasks[i:i + n]
             self.emit(ph)
 
     def dot(self, tasks):
+        """One DOT phase.  In split mode (32-lane groups) every dot of >= 4 terms is computed as two half dots on
+        two lanes and summed by a following LIN phase: halves the dependent multiply chain of the phase."""
         ph = Phase("DOT")
-        ph.tasks = tasks
+        if not self.split:
+            ph.tasks = tasks
+            self.emit(ph)
+            return
+        comb = []
+        for i, (dst, terms) in enumerate(tasks):
+            if len(terms) >= 4:
+                h = (len(terms) + 1) // 2
+                a, b = self.g("SPL.a%d" % i), self.g("SPL.b%d" % i)
+                ph.tasks += [(a, terms[:h]), (b, terms[h:])]
+                comb.append((dst, a, b))
+            else:
+                ph.tasks.append((dst, terms))
         self.emit(ph)
+        if comb:
+            self.lin_rounds([self.lin(dst, (a, 1), (b, 1)) for dst, a, b in comb])
 
     # ---- LIN helpers (return task tuples)
     def kfor(self, slot):
@@ -341,6 +385,71 @@ class Gen:
                     im += [(a[i][0], ds[j]["ty"]), (a[i][1], ds[j]["tx"])]
             tasks += [(d[k][0], re), (d[k][1], im)]
         self.dot(tasks)
+
+    def f12_sqr(self, d, a):
+        """d = a^2 (d distinct from a) by complex squaring over Fp6 = Fp2[v]/(v^3 - xi), v = w^2:
+             a = c0 + c1 w,  c0 = (a0, a2, a4), c1 = (a1, a3, a5)
+             t = c0 c1,  s = (c0 + c1)(c0 + v c1)   ->   a^2 = (s - t - v t) + (2 t) w
+        Two Fp6 products = 12 dots of 6 terms (a general product needs 12 dots of 12 terms)."""
+        assert d is not a
+        with self.pool("TMP", "SQR"):
+            self._f12_sqr(d, a)
+
+    def _f12_sqr(self, d, a):
+        A_ = self.cfg.xi_a
+        c0 = [a[0], a[2], a[4]]
+        c1 = [a[1], a[3], a[5]]
+        S = [self.fp2("SQR.S%d" % j) for j in range(3)]      # c0 + c1
+        B = [self.fp2("SQR.B%d" % j) for j in range(3)]      # c0 + v c1 = (c0_0 + xi c1_2, c0_1 + c1_0, c0_2 + c1_1)
+        lin = []
+        for j in range(3):
+            for c in range(2):
+                lin.append(self.lin(S[j][c], (c0[j][c], 1), (c1[j][c], 1)))
+        # xi * c1_2 = (A x - y, x + A y)
+        lin += [self.lin(B[0][0], (c0[0][0], 1), (c1[2][0], A_), (c1[2][1], -1)),
+                self.lin(B[0][1], (c0[0][1], 1), (c1[2][0], 1), (c1[2][1], A_))]
+        for j in (1, 2):
+            for c in range(2):
+                lin.append(self.lin(B[j][c], (c0[j][c], 1), (c1[j - 1][c], 1)))
+        self.lin_rounds(lin)
+        # derived copies of the second operands (c1 for t, B for s)
+        d1 = [self.der_slots("SQR.d1_%d" % j) for j in range(3)]
+        dB = [self.der_slots("SQR.dB_%d" % j) for j in range(3)]
+        lin = []
+        for j in range(3):
+            lin += self.derived(c1[j], d1[j]) + self.derived(B[j], dB[j])
+        self.lin_rounds(lin)
+
+        def fp6_dots(dst, u, v, dv):
+            """dst = u * v in Fp6; dv = derived copies of v."""
+            out = []
+            for k in range(3):
+                re, im = [], []
+                for i in range(3):
+                    j = (k - i) % 3
+                    if i <= k:  # no wrap
+                        re += [(u[i][0], v[j][0]), (u[i][1], dv[j]["ny"])]
+                        im += [(u[i][0], v[j][1]), (u[i][1], v[j][0])]
+                    else:       # v^3 = xi
+                        re += [(u[i][0], dv[j]["tx"]), (u[i][1], dv[j]["nty"])]
+                        im += [(u[i][0], dv[j]["ty"]), (u[i][1], dv[j]["tx"])]
+                out += [(dst[k][0], re), (dst[k][1], im)]
+            return out
+        Tt = [self.fp2("SQR.T%d" % j) for j in range(3)]
+        Ss = [self.fp2("SQR.P%d" % j) for j in range(3)]
+        self.dot(fp6_dots(Tt, c0, c1, d1) + fp6_dots(Ss, S, B, dB))
+        # new c0 = s - t - v t,  v t = (xi t2, t0, t1);  new c1 = 2 t
+        nc0 = [d[0], d[2], d[4]]
+        nc1 = [d[1], d[3], d[5]]
+        lin = [self.lin(nc0[0][0], (Ss[0][0], 1), (Tt[0][0], -1), (Tt[2][0], -A_), (Tt[2][1], 1)),
+               self.lin(nc0[0][1], (Ss[0][1], 1), (Tt[0][1], -1), (Tt[2][0], -1), (Tt[2][1], -A_))]
+        for j in (1, 2):
+            for c in range(2):
+                lin.append(self.lin(nc0[j][c], (Ss[j][c], 1), (Tt[j][c], -1), (Tt[j - 1][c], -1)))
+        for j in range(3):
+            for c in range(2):
+                lin.append(self.lin(nc1[j][c], (Tt[j][c], 2)))
+        self.lin_rounds(lin)
 
     def f12_sparse(self, d, a, line):
         """d = a * (sum_c line[pos_c] w^pos_c); line: dict pos -> {x, y, ny, tx, ty, nty} slots."""
@@ -544,6 +653,10 @@ def build_miller(gen: Gen):
         gen.lin_rounds(lin)
 
     def add_point(Qx, Qy, nQxy, nQyx, nQyy, Qyy_pos):
+        with gen.pool("TMP", "ADD"):
+            _add_point(Qx, Qy, nQxy, nQyx, nQyy, Qyy_pos)
+
+    def _add_point(Qx, Qy, nQxy, nQyx, nQyy, Qyy_pos):
         """T += Q', Q' = (Qx, Qy) with helper slots nQxy = -Qx.y, nQyx = -Qy.x, nQyy = -Qy.y, Qyy_pos = Qy.y"""
         yqZ, xqZ = gen.fp2("yqZ"), gen.fp2("xqZ")
         t = gen.mul2(yqZ, Qy, Z, nZ1) + gen.mul2(xqZ, Qx, Z, nZ1)
@@ -615,7 +728,7 @@ def build_miller(gen: Gen):
             first = False
             cur = FB
         else:
-            gen.f12_mul(FB, FA, FA)      # FB = FA^2
+            gen.f12_sqr(FB, FA)          # FB = FA^2
             dbl_point()
             gen.f12_sparse(FA, FB, linemap)
             cur = FA
@@ -856,7 +969,7 @@ def build_final_exp(gen: Gen):
 class Sim:
     def __init__(self, gen: Gen):
         self.gen, self.cfg = gen, gen.cfg
-        self.gs = [0] * len(gen.gslots)
+        self.gs = [0] * gen._nslots
         self.maxv = 0
 
     def rd(self, s):
@@ -892,7 +1005,7 @@ class Sim:
 
 def build_all(cfg):
     """Two independent slot files: "M" (MILLER, MUL_AB, MUL_BA) and "F" (FINALEXP)."""
-    gm, gf = Gen(cfg), Gen(cfg)
+    gm, gf = Gen(cfg), Gen(cfg, lanes=32, tm=6, split=True)
     io = {}
     io["miller_in"], io["FA"] = build_miller(gm)
     _, io["FB"], io["GB"] = build_mulacc(gm)
@@ -952,11 +1065,12 @@ def emit_tables(path):
         print(cfg.name, "worst-case value bits per program:", bits, "of", cfg.W * cfg.L)
         for tag, gen in gens.items():
             n = "%s_%s" % (cfg.name, tag)
-            nsg = len(gen.gslots)
+            nsg = gen._nslots
             ref = lambda s, nsg=nsg: s[1] if s[0] == "g" else nsg + s[1]
             out.append("// ---- %s: W=%d L=%d, %d group slots, %d constant slots, %d phases" % (n, cfg.W, cfg.L, nsg, len(gen.cvals), len(gen.phases)))
             out.append("struct %s {" % n)
             out.append("  static constexpr int W = %d, L = %d, NSG = %d, NCONST = %d, NPHASE = %d;" % (cfg.W, cfg.L, nsg, len(gen.cvals), len(gen.phases)))
+            out.append("  static constexpr int LANES = %d, TM = %d, REC = %d;  // lanes per group, max DOT terms, u16 per lane record" % (gen.lanes, gen.tm, 2 * gen.tm + 2))
             out.append("  static constexpr uint32_t N0 = 0x%xu;" % cfg.n0)
             out.append("  static constexpr int FP_BYTES = %d;" % (32 if cfg.name == "BN254" else 48))
             out.append("  HD static constexpr uint32_t p(int i) {")
@@ -983,34 +1097,36 @@ def emit_tables(path):
             for v in gen.cvals:
                 out.append("  {%s}," % ", ".join("0x%xu" % x for x in v))
             out.append("};")
-            # phase header: kind (0 DOT, 1 LIN) | T << 8 | ntasks << 16; record: 26 x u16 per lane:
-            #   [0] dst (0xFFFF = idle), [1..12] a / source slots, [13..24] b slots / LIN coefficient words, [25] pad
+            # phase header: kind (0 DOT, 1 LIN) | T << 8 | ntasks << 16; record: REC = 2 TM + 2 u16 per lane:
+            #   [0] dst (0xFFFF = idle), [1..TM] a / source slots, [1+TM..2TM] b slots / LIN coefficient words, [2TM+1] pad
+            TM, REC = gen.tm, 2 * gen.tm + 2
             hdr, rec = [], []
             for ph in gen.phases:
                 hdr.append((0 if ph.kind == "DOT" else 1) | (ph.T << 8) | (len(ph.tasks) << 16))
-                for lane in range(G):
-                    r = [0xFFFF] + [ref(gen.ZERO)] * 24 + [0]
+                for lane in range(gen.lanes):
+                    r = [0xFFFF] + [ref(gen.ZERO)] * (2 * TM) + [0]
                     if ph.kind == "LIN":
-                        for t in range(12):
-                            r[13 + t] = 0
+                        for t in range(TM):
+                            r[1 + TM + t] = 0
                     if lane < len(ph.tasks):
                         dst, terms = ph.tasks[lane]
                         r[0] = ref(dst)
                         for t, term in enumerate(terms):
                             if ph.kind == "DOT":
-                                r[1 + t], r[13 + t] = ref(term[0]), ref(term[1])
+                                r[1 + t], r[1 + TM + t] = ref(term[0]), ref(term[1])
                             else:
                                 slot, coef, K = term
                                 r[1 + t] = ref(slot)
                                 # |coef| in bits 0..6, sign in bit 7, KP constant index in bits 8..15
                                 kp = gen.KP[K][1] if coef < 0 else 0
                                 assert abs(coef) < 128 and kp < 256
-                                r[13 + t] = abs(coef) | (0x80 if coef < 0 else 0) | (kp << 8)
+                                r[1 + TM + t] = abs(coef) | (0x80 if coef < 0 else 0) | (kp << 8)
+                    assert len(r) == REC
                     rec += r
             out.append("static const uint32_t %s_PHASE_HDR[%d] = {%s};" % (n, len(hdr), ", ".join(str(h) for h in hdr)))
             out.append("static const uint16_t %s_PHASE_REC[%d] = {" % (n, len(rec)))
-            for i in range(0, len(rec), 26):
-                out.append("  " + ",".join(str(x) for x in rec[i:i + 26]) + ",")
+            for i in range(0, len(rec), REC):
+                out.append("  " + ",".join(str(x) for x in rec[i:i + REC]) + ",")
             out.append("};")
             for pname, prog in gen.programs.items():
                 out.append("static const uint16_t %s_PROG_%s[%d] = {%s};" % (n, pname, len(prog), ",".join(str(x) for x in prog)))
