@@ -1,0 +1,99 @@
+"""BASELINE.json-size cases on the GPU through size-independent properties (the oracle would take
+minutes at these sizes): inputs are produced by the engine's own ScalePoints kernel with known
+discrete logs, spot-checked against the oracle, and the verdicts / sums must follow."""
+import random
+
+import pytest
+
+from oracle import c_oracle as C
+from parity_util import CURVES, scalars_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import bgls_b200
+    c = bgls_b200.Context(0)
+    yield c
+    c.close()
+
+
+def synth_aggregate(ctx, cid, c, n, seed):
+    """(g1, g2) of a valid n-signer aggregate (n+1 pairs) built on the GPU: H_i = h_i G1, pk_i = s_i G2."""
+    rng = random.Random(seed)
+    hs = [rng.randrange(1, c.r) for _ in range(n)]
+    ss = [rng.randrange(1, c.r) for _ in range(n)]
+    g1 = ctx.scale_points(cid, 1, c.marshal_g1(c.g1) * n, scalars_bytes(hs), n)
+    g2 = ctx.scale_points(cid, 2, c.marshal_g2(c.g2) * n, scalars_bytes(ss), n)
+    tot = sum(h * s for h, s in zip(hs, ss)) % c.r
+    neg = ctx.scale_points(cid, 1, c.marshal_g1(c.g1), scalars_bytes([(c.r - tot) % c.r]), 1)
+    # spot-check the generated points against the oracle
+    nb = c.nbytes
+    for i in (0, n // 2, n - 1):
+        assert g1[2 * nb * i:2 * nb * (i + 1)] == C.scale_points(cid, 1, c.marshal_g1(c.g1), scalars_bytes([hs[i]]), 1)
+        assert g2[4 * nb * i:4 * nb * (i + 1)] == C.scale_points(cid, 2, c.marshal_g2(c.g2), scalars_bytes([ss[i]]), 1)
+    return g1 + neg, g2 + c.marshal_g2(c.g2)
+
+
+def test_config3_multisig_65536_g2_keys(ctx):
+    """config 3: bls12-381 multi-signature verify, 65,536 signers: AggregatePoints over 12 MiB of G2 keys
+    (bit-exact against the oracle sum and against (sum k_i) G2), then the 2-pairing check."""
+    cid, c = CURVES[1]
+    n = 65536
+    rng = random.Random(3)
+    ks = [rng.randrange(1, c.r) for _ in range(n)]
+    keys = ctx.scale_points(cid, 2, c.marshal_g2(c.g2) * n, scalars_bytes(ks), n)
+    agg = ctx.aggregate_points(cid, 2, keys, n)
+    ksum = sum(ks) % c.r
+    assert agg == C.scale_points(cid, 2, c.marshal_g2(c.g2), scalars_bytes([ksum]), 1)
+    assert agg == C.aggregate(cid, 2, keys, n, 8)
+    # multi-signature on one message: sigma = (sum k_i) H ; e(-H, agg) e(sigma, g2) == 1  (bgls/bgls.go:65-70,89-92)
+    h = rng.randrange(1, c.r)
+    H = C.scale_points(cid, 1, c.marshal_g1(c.g1), scalars_bytes([h]), 1)
+    negH = C.scale_points(cid, 1, c.marshal_g1(c.g1), scalars_bytes([(c.r - h) % c.r]), 1)
+    sigma = C.scale_points(cid, 1, H, scalars_bytes([ksum]), 1)
+    gt, ok = ctx.pairing_product(cid, negH + sigma, agg + c.marshal_g2(c.g2), 2)
+    assert ok and gt == c.marshal_gt(c.fp12_one)
+    _, ok = ctx.pairing_product(cid, negH + sigma, keys[:192] + c.marshal_g2(c.g2), 2)
+    assert not ok
+
+
+@pytest.mark.parametrize("cid,c,n", [(0, CURVES[0][1], 40000), (1, CURVES[1][1], 131072)])
+def test_large_aggregate_verify_and_sharding(ctx, cid, c, n):
+    """config 4 per-GPU share (bls12-381, 2^20 / 8 = 131,072 signers) and a large altbn128 product: valid
+    aggregate -> identity; one swapped message -> reject; product of two shard Miller products == unsharded."""
+    g1, g2 = synth_aggregate(ctx, cid, c, n, 1000 + cid)
+    gt, ok = ctx.pairing_product(cid, g1, g2, n + 1)
+    assert ok and gt == c.marshal_gt(c.fp12_one)
+    nb = c.nbytes
+    bad = g1[2 * nb:4 * nb] + g1[2 * nb:]
+    gt_bad, ok = ctx.pairing_product(cid, bad, g2, n + 1)
+    assert not ok
+    half = (n + 1) // 2
+    parts = ctx.miller_product(cid, g1[:2 * nb * half], g2[:4 * nb * half], half) + \
+        ctx.miller_product(cid, g1[2 * nb * half:], g2[4 * nb * half:], n + 1 - half)
+    gt2, ok2 = ctx.final_exp_product(cid, parts, 2)
+    assert ok2 and gt2 == gt
+    # the rejected product is still a deterministic GT element: both engines' regimes must agree on it
+    small = 4000
+    gts, _ = ctx.pairing_product(cid, bad[:2 * nb * small], g2[:4 * nb * small], small)
+    assert gts == C.pairing_product(cid, bad[:2 * nb * small], g2[:4 * nb * small], small, 8, 0)
+
+
+def test_config5_batch_of_independent_verifies(ctx):
+    """config 5 shape (independent altbn128 aggregate verifies, throughput mode): 512 checks x 65 pairs with a
+    known pattern of corrupted signatures."""
+    cid, c = CURVES[0]
+    nb = c.nbytes
+    signers, nbatch = 64, 512
+    g1, g2 = synth_aggregate(ctx, cid, c, signers, 77)
+    G1, G2, offsets, expect = [], [], [0], []
+    for b in range(nbatch):
+        good = (b % 7) != 3
+        a1 = g1 if good else g1[:-2 * nb] + c.marshal_g1(c.g1)
+        G1.append(a1)
+        G2.append(g2)
+        offsets.append(offsets[-1] + signers + 1)
+        expect.append(good)
+    assert ctx.pairing_check_batch(cid, b"".join(G1), b"".join(G2), offsets) == expect
