@@ -172,6 +172,110 @@ template <class M> HD void mach_canon_be(uint8_t* be, const uint32_t* limbs, boo
     *is_one = nz == 0;
 }
 
+// ---- 32-bit word helpers for the single-lane inverse
+template <class M> HD void mach_limbs_to_words(uint32_t* w, const uint32_t* v) {
+    constexpr int NW = M::FP_BYTES / 4, L = M::L, W = M::W;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const int bit = 32 * k, li = bit / W, sh = bit % W;
+        unsigned long long x = (unsigned long long)v[li] >> sh;
+        if (li + 1 < L) x |= (unsigned long long)v[li + 1] << (W - sh);
+        if (li + 2 < L && 2 * W - sh < 32) x |= (unsigned long long)v[li + 2] << (2 * W - sh);
+        w[k] = (uint32_t)x;
+    }
+}
+template <class M> HD void mach_words_to_limbs(uint32_t* out, const uint32_t* win) {
+    constexpr int NW = M::FP_BYTES / 4, L = M::L, W = M::W;
+    constexpr uint32_t MASK = (1u << W) - 1;
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = win[i];
+    w[NW] = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const int bit = W * i, wi = bit >> 5, sh = bit & 31;
+        const uint32_t lo = w[wi], hi = w[wi + 1];
+        out[i] = (sh ? ((lo >> sh) | (hi << (32 - sh))) : lo) & MASK;
+    }
+}
+template <int NW> HD uint32_t w_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) { c += (unsigned long long)a[i] + b[i]; r[i] = (uint32_t)c; c >>= 32; }
+    return (uint32_t)c;
+}
+template <int NW> HD uint32_t w_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    long long c = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) { c += (long long)a[i] - (long long)b[i]; r[i] = (uint32_t)c; c >>= 32; }
+    return c != 0;  // borrow
+}
+template <int NW> HD void w_shr1(uint32_t* a, uint32_t top) {
+#pragma unroll
+    for (int i = 0; i < NW - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[NW - 1] = (a[NW - 1] >> 1) | (top << 31);
+}
+template <int NW> HD bool w_geq(const uint32_t* a, const uint32_t* b) {
+    for (int i = NW - 1; i >= 0; i--) {
+        if (a[i] != b[i]) return a[i] > b[i];
+    }
+    return true;
+}
+template <int NW> HD bool w_is_one(const uint32_t* a) {
+    uint32_t x = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < NW; i++) x |= a[i];
+    return x == 0;
+}
+// out = in^-1 mod p; in: plain-domain value < 2p as L limbs, out: L limbs < p (0 -> 0).
+// Binary extended Euclid (right-shift variant, p odd): ~2 log2(p) shift/subtract steps on one lane instead of
+// the ~380 dependent Montgomery multiplications of a Fermat inversion.
+template <class M> HD void mach_inv(uint32_t* out, const uint32_t* in) {
+    constexpr int NW = M::FP_BYTES / 4, L = M::L;
+    uint32_t P[NW], u[NW], v[NW], x1[NW], x2[NW], t[NW];
+    uint32_t pl[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) pl[i] = M::p(i);
+    mach_limbs_to_words<M>(P, pl);
+    mach_limbs_to_words<M>(u, in);
+    if (!w_sub<NW>(t, u, P)) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) u[i] = t[i];
+    }
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) { v[i] = P[i]; x1[i] = 0; x2[i] = 0; nz |= u[i]; }
+    x1[0] = 1;
+    if (nz != 0) {
+        for (int guard = 0; guard < 4 * 32 * NW && !w_is_one<NW>(u) && !w_is_one<NW>(v); guard++) {
+            if ((u[0] & 1u) == 0) {
+                w_shr1<NW>(u, 0);
+                uint32_t c = 0;
+                if (x1[0] & 1u) c = w_add<NW>(x1, x1, P);
+                w_shr1<NW>(x1, c);
+            } else if ((v[0] & 1u) == 0) {
+                w_shr1<NW>(v, 0);
+                uint32_t c = 0;
+                if (x2[0] & 1u) c = w_add<NW>(x2, x2, P);
+                w_shr1<NW>(x2, c);
+            } else if (w_geq<NW>(u, v)) {
+                w_sub<NW>(u, u, v);
+                if (w_sub<NW>(x1, x1, x2)) w_add<NW>(x1, x1, P);
+            } else {
+                w_sub<NW>(v, v, u);
+                if (w_sub<NW>(x2, x2, x1)) w_add<NW>(x2, x2, P);
+            }
+        }
+        const bool use1 = w_is_one<NW>(u);
+#pragma unroll
+        for (int i = 0; i < NW; i++) t[i] = use1 ? x1[i] : x2[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; i++) t[i] = 0;
+    }
+    mach_words_to_limbs<M>(out, t);
+}
+
 // ---- tables on the device: one struct of pointers per slot file
 struct MachTables {
     const uint32_t* consts;   // [NCONST][L]
@@ -185,7 +289,17 @@ template <class M> HD void mach_phase_lane(const MachView<M>& mv, const MachTabl
     const int T = (h >> 8) & 0xFF;
     const uint16_t* rec = tb.rec + ((size_t)phase * M::LANES + lane) * M::REC;
     uint32_t out[M::L];
-    if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, T, out);
+    const uint32_t kind = h & 0xFF;
+    if (kind == 2) {  // single-lane modular inverse
+        if (rec[0] != MIDLE) {
+            uint32_t in[M::L];
+            mach_load<M>(in, mv, rec[1]);
+            mach_inv<M>(out, in);
+            mach_store<M>(mv, rec[0], out);
+        }
+        return;
+    }
+    if (kind == 0) mach_dot<M>(mv, rec, T, out);
     else mach_lin<M>(mv, rec, T, out);
     if (rec[0] != MIDLE) mach_store<M>(mv, rec[0], out);
 }

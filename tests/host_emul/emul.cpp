@@ -82,7 +82,9 @@ template <class M, class T> struct HostMach {
             uint32_t outs[M::LANES][M::L];
             for (int lane = 0; lane < M::LANES; lane++) {
                 const uint16_t* rec = tb.rec + ((size_t)ph * M::LANES + lane) * M::REC;
-                if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, Tn, outs[lane]);
+                if ((h & 0xFF) == 2) {
+                    if (rec[0] != MIDLE) { uint32_t in[M::L]; mach_load<M>(in, mv, rec[1]); mach_inv<M>(outs[lane], in); }
+                } else if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, Tn, outs[lane]);
                 else mach_lin<M>(mv, rec, Tn, outs[lane]);
             }
             for (int lane = 0; lane < M::LANES; lane++) {  // deferred stores: a phase must be hazard-free

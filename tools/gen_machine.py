@@ -99,7 +99,7 @@ def f2inv(a, p):
 
 class Phase:
     def __init__(self, kind):
-        self.kind = kind  # "DOT" | "LIN"
+        self.kind = kind  # "DOT" | "LIN" | "INV" (single-lane modular inverse of a plain-domain value)
         self.tasks = []   # (dst, terms)  DOT terms: (a, b); LIN terms: (slot, coef, K)
 
     @property
@@ -207,7 +207,9 @@ class Gen:
                 reads.add(t[0])
                 if phase.kind == "DOT":
                     reads.add(t[1])
-        if phase.kind == "DOT":
+        if phase.kind == "INV":
+            assert len(phase.tasks) == 1 and len(phase.tasks[0][1]) == 1
+        elif phase.kind == "DOT":
             assert not (reads & set(dsts)), "DOT phase reads a slot it writes"
             assert phase.T <= self.tm
         else:
@@ -223,6 +225,10 @@ class Gen:
         # static bounds
         new_ub = {}
         for dst, terms in phase.tasks:
+            if phase.kind == "INV":
+                assert self.ub.get(terms[0][0]) is not None and self.ub[terms[0][0]] < 2 * cfg.p, "INV input must be < 2p"
+                new_ub[dst] = cfg.p - 1
+                continue
             if phase.kind == "DOT":
                 s = 0
                 for a, b in terms:
@@ -266,6 +272,10 @@ class Gen:
             ph = self.phases[pid]
             new = {}
             for dst, terms in ph.tasks:
+                if ph.kind == "INV":
+                    assert ub.get(terms[0][0]) is not None and ub[terms[0][0]] < 2 * cfg.p, ("INV input must be < 2p", prog, pid)
+                    new[dst] = cfg.p - 1
+                    continue
                 if ph.kind == "DOT":
                     acc = 0
                     for a, b in terms:
@@ -286,6 +296,16 @@ class Gen:
                 new[dst] = v
             ub.update(new)
         return worst, ub
+
+    def inv(self, dst, src):
+        """dst = src^-1 in Montgomery form (src in Montgomery form, any bounded representative):
+        out of Montgomery form (DOT by the plain 1), binary extended GCD on one lane, back (DOT by R^2)."""
+        t0, t1 = self.g("INVOP.t0"), self.g("INVOP.t1")
+        self.dot([(t0, [(src, self.RAW1)])])
+        ph = Phase("INV")
+        ph.tasks = [(t1, [(t0,)])]
+        self.emit(ph)
+        self.dot([(dst, [(t1, self.R2)])])
 
     def lin_rounds(self, tasks):
         """LIN tasks, 16 per phase (a later round must not read what an earlier round wrote)."""
@@ -846,18 +866,9 @@ def build_final_exp(gen: Gen):
     # Fp2 inverse of n: nn = n.x^2 + n.y^2 ; n^-1 = (n.x, -n.y) / nn
     nn = gen.g("INV.nn")
     gen.dot([(nn, [(n[0], n[0]), (n[1], n[1])])])
-    # Fermat: nn^(p-2), square-and-multiply, ping-pong between two slots
-    s = [gen.g("INV.s0"), gen.g("INV.s1")]
-    gen.lin_rounds([gen.lin(s[0], (nn, 1))])
-    cur = 0
-    bits = bin(p - 2)[3:]
-    for bch in bits:
-        gen.dot([(s[1 - cur], [(s[cur], s[cur])])])
-        cur = 1 - cur
-        if bch == "1":
-            gen.dot([(s[1 - cur], [(s[cur], nn)])])
-            cur = 1 - cur
-    inv = s[cur]
+    # Fp inverse of the norm: one single-lane binary-GCD phase (a Fermat chain would be ~380 dependent DOT phases)
+    inv = gen.g("INV.inv")
+    gen.inv(inv, nn)
     ni = gen.fp2("INV.ni")
     nny = gen.g("INV.nny")
     gen.lin_rounds([gen.lin(nny, (n[1], -1))])
@@ -982,6 +993,10 @@ class Sim:
             ph = self.gen.phases[pid]
             outs = []
             for dst, terms in ph.tasks:
+                if ph.kind == "INV":
+                    v = pow(self.rd(terms[0][0]) % cfg.p, -1, cfg.p)
+                    outs.append((dst, v))
+                    continue
                 if ph.kind == "DOT":
                     t = sum(self.rd(a) * self.rd(b) for a, b in terms)
                     m = (-t * pinv) % cfg.R
@@ -1102,7 +1117,7 @@ def emit_tables(path):
             TM, REC = gen.tm, 2 * gen.tm + 2
             hdr, rec = [], []
             for ph in gen.phases:
-                hdr.append((0 if ph.kind == "DOT" else 1) | (ph.T << 8) | (len(ph.tasks) << 16))
+                hdr.append({"DOT": 0, "LIN": 1, "INV": 2}[ph.kind] | (ph.T << 8) | (len(ph.tasks) << 16))
                 for lane in range(gen.lanes):
                     r = [0xFFFF] + [ref(gen.ZERO)] * (2 * TM) + [0]
                     if ph.kind == "LIN":
@@ -1112,7 +1127,9 @@ def emit_tables(path):
                         dst, terms = ph.tasks[lane]
                         r[0] = ref(dst)
                         for t, term in enumerate(terms):
-                            if ph.kind == "DOT":
+                            if ph.kind == "INV":
+                                r[1] = ref(term[0])
+                            elif ph.kind == "DOT":
                                 r[1 + t], r[1 + TM + t] = ref(term[0]), ref(term[1])
                             else:
                                 slot, coef, K = term
