@@ -18,7 +18,7 @@ EXPORTS = [
     "bgls_ctx_create", "bgls_ctx_destroy", "bgls_last_error", "bgls_version", "bgls_pairing_product", "bgls_pair",
     "bgls_gt_mul", "bgls_aggregate_points", "bgls_scale_points", "bgls_miller_product", "bgls_final_exp_product",
     "bgls_pairing_check_batch", "bgls_pairing_product_dev", "bgls_miller_product_dev", "bgls_final_exp_product_dev",
-    "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
+    "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_hash_to_g1", "bgls_hash_to_g1_dev", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
 ]
 
 _lib = None
@@ -57,6 +57,8 @@ def load():
     L.bgls_aggregate_points_dev.argtypes = [vp, i, i, vp, sz, vp, vp]
     L.bgls_scale_points_dev.argtypes = [vp, i, i, vp, vp, sz, vp, vp]
     L.bgls_pairing_check_batch_dev.argtypes = [vp, i, vp, vp, vp, sz, sz, vp, vp]
+    L.bgls_hash_to_g1.argtypes = [vp, i, cp, ctypes.POINTER(ctypes.c_uint64), sz, cp]
+    L.bgls_hash_to_g1_dev.argtypes = [vp, i, vp, vp, sz, vp, vp]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
     L.bgls_set_profiling.argtypes = [vp, i]
@@ -150,6 +152,18 @@ class Context:
         flag = ctypes.c_int(0)
         self._chk(self._L.bgls_final_exp_product(self._h, curve, partials, k, out, ctypes.byref(flag)))
         return out.raw, bool(flag.value)
+
+    def hash_to_g1(self, curve, msgs) -> bytes:
+        """HashToG1 of every message (list of bytes) -> concatenated uncompressed G1 records."""
+        n = len(msgs)
+        offs = [0]
+        for m in msgs:
+            offs.append(offs[-1] + len(m))
+        off = (ctypes.c_uint64 * (n + 1))(*offs)
+        blob = b"".join(bytes(m) for m in msgs) or b"\0"
+        out = ctypes.create_string_buffer(max(1, n * 2 * FP_BYTES[curve]))
+        self._chk(self._L.bgls_hash_to_g1(self._h, curve, blob, off, n, out))
+        return out.raw[: n * 2 * FP_BYTES[curve]]
 
     def pairing_check_batch(self, curve, g1: bytes, g2: bytes, offsets) -> list:
         nb = len(offsets) - 1

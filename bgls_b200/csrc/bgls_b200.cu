@@ -15,10 +15,12 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/bgls_b200.h"
 #include "pairing.cuh"
 #include "machine_kernels.cuh"
+#include "hash.cuh"
 
 namespace bgls {
 
@@ -161,6 +163,18 @@ __global__ void __launch_bounds__(TB) k_scale(const uint8_t* __restrict__ pts, c
     jac_load<C>(p, pts + i * rec);
     jac_mul(r, p, scalars + 32 * i);
     jac_store<C>(out + i * rec, r);
+}
+
+// hash-to-G1, one message per thread (messages concatenated, offsets[n+1])
+template <class C>
+__global__ void __launch_bounds__(TB) k_hash_to_g1(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
+                                                   uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* m = msgs + off[i];
+    const size_t len = (size_t)(off[i + 1] - off[i]);
+    if constexpr (C::IS_BN) hash_to_g1_keccak_ti<C>(out + i * 2 * C::FP_BYTES, m, len);
+    else hash_to_g1_ft<C>(out + i * 2 * C::FP_BYTES, m, len);
 }
 
 // register-only IMAD.WIDE.U32 loop: the integer-pipe roofline denominator.  The multiplier operand is
@@ -721,6 +735,44 @@ int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, c
     CU(cudaMemcpyAsync(out, dout, n * rec, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return BGLS_OK;
+}
+static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_off, size_t n, void* d_out, cudaStream_t s) {
+    if (n == 0) return BGLS_OK;
+    const unsigned nb = (unsigned)((n + TB - 1) / TB);
+    if (curve == BGLS_ALTBN128) k_hash_to_g1<BN254><<<nb, TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    else k_hash_to_g1<BLS381><<<nb, TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+int bgls_hash_to_g1(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_t* offsets, size_t n, uint8_t* out) {
+    if (!ctx || !curve_ok(curve) || !offsets || (n && !out)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    if (n == 0) return BGLS_OK;
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, BGLS_ERR_ARG, "offsets not monotone");
+    const size_t total = offsets[n] - offsets[0];
+    if (total && !msgs) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), bm = align_up(total + 16), bo = align_up((n + 1) * 8), bp = align_up(n * 2 * F);
+    int rc = ensure_scratch(ctx, bm + bo + bp);
+    if (rc) return rc;
+    uint8_t *dm = (uint8_t*)ctx->scratch, *doff = dm + bm, *dout = doff + bo;
+    std::vector<uint64_t> rel(n + 1);
+    for (size_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+    if (total) CU(cudaMemcpyAsync(dm, msgs + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(doff, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = hash_dev(ctx, curve, dm, doff, n, dout, ctx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, dout, n * 2 * F, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BGLS_OK;
+}
+int bgls_hash_to_g1_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_offsets, size_t n, void* d_out, void* stream) {
+    if (!ctx || !curve_ok(curve) || (n && (!d_offsets || !d_out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Guard g(ctx);
+    CU(cudaSetDevice(ctx->device));
+    return hash_dev(ctx, curve, d_msgs, d_offsets, n, d_out, (cudaStream_t)stream);
 }
 int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, const uint64_t* offsets,
                              size_t nbatch, uint8_t* out_ok) {

@@ -76,6 +76,12 @@ int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pt
 int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, const uint8_t* scalars,
                       size_t n, uint8_t* out);
 
+/* CurveSystem.HashToG1 -- curves/altbn128.go:509-513 (Keccak-256 try-and-increment, curves/hash.go:53-77) and
+ * curves/bls12_381.go:349-351 (blake2b + Fouque-Tibouchi + cofactor, curves/hash.go:79-167): the pre-step of
+ * verifyAggSig (bgls/bgls.go:106-111), one message per GPU thread.  Message i is msgs[offsets[i] .. offsets[i+1]);
+ * out receives n uncompressed G1 records. */
+int bgls_hash_to_g1(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_t* offsets, size_t n, uint8_t* out);
+
 /* Signer-set sharding: product of the *Miller values* of n pairs without the
  * final exponentiation (GT layout, 12*F bytes).  Partials from several GPUs are exchanged
  * (e.g. NCCL all-gather) and finished with bgls_final_exp_product. */
@@ -102,6 +108,8 @@ int bgls_aggregate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d
                               void* stream);
 int bgls_scale_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void* d_scalars,
                           size_t n, void* d_out, void* stream);
+int bgls_hash_to_g1_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_offsets, size_t n, void* d_out,
+                        void* stream);
 int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2,
                                  const void* d_offsets, size_t nbatch, size_t total_pairs, void* d_out_ok,
                                  void* stream);

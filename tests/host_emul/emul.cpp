@@ -167,3 +167,10 @@ extern "C" int emu_mach_pairing_product(int curve, const uint8_t* g1, const uint
     if (curve == 0) return mach_pairing<BN254_M, BN254_M_T, BN254_F, BN254_F_T>(g1, g2, n, out, do_final, dbg_f);
     return mach_pairing<BLS381_M, BLS381_M_T, BLS381_F, BLS381_F_T>(g1, g2, n, out, do_final, dbg_f);
 }
+
+// ============================================================ hash-to-G1 (host emulation of the device functions)
+#include "../../bgls_b200/csrc/hash.cuh"
+extern "C" void emu_hash_to_g1(int curve, const uint8_t* msg, size_t len, uint8_t* out) {
+    if (curve == 0) hash_to_g1_keccak_ti<BN254>(out, msg, len);
+    else hash_to_g1_ft<BLS381>(out, msg, len);
+}

@@ -183,3 +183,75 @@ def test_aggregate_verify_config_shape(ctx, cid, c):
     bad = g1[2 * nb:4 * nb] + g1[2 * nb:]
     gt, ok = ctx.pairing_product(cid, bad, g2, n + 1)
     assert not ok and gt == C.pairing_product(cid, bad, g2, n + 1, 8, 0)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_hash_to_g1_reference_vectors_gpu(ctx, cid, c):
+    """curves/curve_test.go:210-244 (TestG1HashVectors), curves/altbn128_test.go:13-24, curves/bls12_test.go:57-67
+    through bgls_hash_to_g1, plus ragged lengths against the oracle in one batched call."""
+    import base64
+    import os
+    fname = "altbn128G1Hash.dat" if cid == 0 else "bls12G1Hash.dat"
+    msgs, want = [], []
+    for line in open(os.path.join(os.path.dirname(__file__), "golden", fname)):
+        m, pt = line.strip().split(",")
+        msgs.append(base64.b64decode(m))
+        want.append(base64.b64decode(pt))
+    rng = random.Random(4)
+    for ln in (0, 1, 31, 32, 64, 127, 128, 135, 136, 137, 255, 300):
+        m = bytes(rng.randrange(256) for _ in range(ln))
+        msgs.append(m)
+        want.append(c.marshal_g1(c.hash_to_g1(m)))
+    if cid == 0:
+        a = 9121282642809701931333593728297233225556711250127745709186816755779879923737
+        msgs.append(a.to_bytes(32, "big"))
+        want.append((11423386531623885114587219621463106117140760157404497425836076043015227528156).to_bytes(32, "big") +
+                    (20262289731964024720969923714809935701428881933342918937283877214228227624643).to_bytes(32, "big"))
+    got = ctx.hash_to_g1(cid, msgs)
+    rec = 2 * c.nbytes
+    for i, w in enumerate(want):
+        assert got[i * rec:(i + 1) * rec] == w, i
+
+
+def test_scheme_layer_end_to_end():
+    """bgls/bgls_test.go:19-77 (TestSingleSigner, TestAggregation) and bgls/blsKosk_test.go multisig shape, written
+    against the engine-backed mirror of the reference API: every hash, scalar multiplication, point sum and pairing
+    runs on the GPU."""
+    from bgls_b200 import bgls
+    from bgls_b200.curves import Altbn128, Bls12
+    rng = random.Random(2018)
+    for curve in (Altbn128, Bls12):
+        sk, vk, err = bgls.KeyGen(curve, rng)
+        assert err is None
+        d = bytes(rng.randrange(256) for _ in range(64))
+        sig = bgls.Sign(curve, sk, d)
+        assert bgls.VerifySingleSignature(curve, sig, vk, d)
+        sig2, _ = sig.Copy().Add(curve.GetG1())
+        assert not bgls.VerifySingleSignature(curve, sig2, vk, d)
+        N = 6
+        msgs = [bytes(rng.randrange(256) for _ in range(32)) for _ in range(N)]
+        keys = [bgls.KeyGen(curve, rng) for _ in range(N)]
+        sigs = [bgls.Sign(curve, k[0], m) for k, m in zip(keys, msgs)]
+        pubs = [k[1] for k in keys]
+        agg = bgls.AggregateSignatures(sigs)
+        assert bgls.VerifyAggregateSignature(curve, agg, pubs, msgs)
+        assert not bgls.VerifyAggregateSignature(curve, agg, pubs[:N - 1], msgs)
+        skf, vkf, _ = bgls.KeyGen(curve, rng)
+        agg2 = bgls.AggregateSignatures(sigs + [bgls.Sign(curve, skf, msgs[0])])
+        assert not bgls.VerifyAggregateSignature(curve, agg2, pubs + [vkf], msgs + [msgs[0]])   # duplicate message
+        assert not bgls.VerifyAggregateSignature(curve, agg2, pubs, msgs)                        # wrong signature
+        assert not bgls.VerifyAggregateSignature(curve, agg, pubs, [msgs[1], msgs[0]] + msgs[2:])  # swapped
+        # Kosk multi-signature: 8 signers, one message (bgls/blsKosk_test.go:35-64)
+        m = bytes(rng.randrange(256) for _ in range(64))
+        ks = [bgls.KeyGen(curve, rng) for _ in range(8)]
+        msig = bgls.AggregateSignatures([bgls.KoskSign(curve, k[0], m) for k in ks])
+        assert bgls.KoskVerifyMultiSignature(curve, msig, [k[1] for k in ks], m)
+        assert not bgls.KoskVerifyMultiSignature(curve, msig, [k[1] for k in ks[:-1]], m)
+        # TestMul / TestAggregation of the curves package on the mirror (curves/curve_test.go:120-186)
+        k = rng.randrange(curve.GetG1Order())
+        inf, ok = curve.GetG1().Mul(k).Add(curve.GetG1().Mul(-k))
+        assert ok and inf.Equals(curve.GetG1Infinity())
+        gt, ok = curve.PairingProduct([curve.GetG1()], [curve.GetG2(), curve.GetG2()])
+        assert gt is None and not ok      # length mismatch (curves/curve.go:126-128)
+        assert curve.Pair(curve.GetG2(), curve.GetG2()) == (None, False)   # type mismatch (curves/altbn128.go:131-140)
+        assert curve.Pair(curve.GetG1(), curve.GetG2Infinity())[0].Equals(curve.GetGTIdentity())

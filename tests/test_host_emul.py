@@ -94,3 +94,33 @@ def test_machine_interpreter_and_programs(E, cid, c):
     assert E.emu_mach_pairing_product(cid, G1, G2, 5, out, 1, None) == 1
     assert out.raw == c.marshal_gt(c.fp12_one)
     assert E.emu_mach_pairing_product(cid, b"", b"", 0, out, 1, None) == 1
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_hash_to_g1_reference_vectors(E, cid, c):
+    """The device hash-to-G1 functions against the reference's own vectors (curves/curve_test.go:210-244,
+    curves/altbn128_test.go:13-24, curves/bls12_test.go:57-67) and against the oracle on ragged lengths."""
+    import base64
+    E.emu_hash_to_g1.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    nb = c.nbytes
+
+    def H(m):
+        out = ctypes.create_string_buffer(2 * nb)
+        E.emu_hash_to_g1(cid, m, len(m), out)
+        return out.raw
+    fname = "altbn128G1Hash.dat" if cid == 0 else "bls12G1Hash.dat"
+    for line in open(os.path.join(HERE, "golden", fname)):
+        m, pt = line.strip().split(",")
+        assert H(base64.b64decode(m)) == base64.b64decode(pt)
+    if cid == 0:
+        a = 9121282642809701931333593728297233225556711250127745709186816755779879923737
+        got = H(a.to_bytes(32, "big"))
+        assert int.from_bytes(got[:32], "big") == 11423386531623885114587219621463106117140760157404497425836076043015227528156
+        assert int.from_bytes(got[32:], "big") == 20262289731964024720969923714809935701428881933342918937283877214228227624643
+    else:
+        got = H(b"")
+        assert int.from_bytes(got[:48], "big") == 315124130825307604287835216317628428134609737854237653839182597515996444073032649481416725367158979153513345579672
+    rng = random.Random(17)
+    for ln in (0, 1, 31, 32, 123, 124, 127, 128, 135, 136, 137, 200, 300):
+        m = bytes(rng.randrange(256) for _ in range(ln))
+        assert H(m) == c.marshal_g1(c.hash_to_g1(m)), ln

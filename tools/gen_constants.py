@@ -32,7 +32,7 @@ def f2inv(a, p):
     return (a[0] * n % p, -a[1] * n % p)
 
 
-def emit(name, p, r, xi, b, twist, n, extra):
+def emit(name, p, r, xi, b, twist, n, extra, extra_consts=()):
     R = 1 << (32 * n)
     mont = lambda v: limbs(v * R % p, n)
     mont2 = lambda a: mont(a[0]) + mont(a[1])
@@ -66,6 +66,10 @@ def emit(name, p, r, xi, b, twist, n, extra):
     out.append(f"DEVCONST uint32_t {U}_GAMMA2[6][{n}] = {{" + ", ".join(arr(mont(g[0])) for g in g2) + "};")
     out.append(f"DEVCONST uint32_t {U}_GAMMA3[6][{2 * n}] = {{" + ", ".join(arr(mont2(g)) for g in g3) + "};")
     out.append(f"DEVCONST uint32_t {U}_PM2[{n}] = {arr(limbs(p - 2, n))};  // exponent for Fermat inversion")
+    out.append(f"DEVCONST uint32_t {U}_PP1D4[{n}] = {arr(limbs((p + 1) // 4, n))};  // square root exponent (p = 3 mod 4)")
+    out.append(f"DEVCONST uint32_t {U}_PM1D2[{n}] = {arr(limbs((p - 1) // 2, n))};  // Euler criterion exponent, also the parity threshold")
+    for cname, cval in extra_consts:
+        out.append(f"DEVCONST uint32_t {U}_{cname}[{n}] = {arr(mont(cval))};")
     out.append(f"struct {name} {{")
     out.append(f"    static constexpr int N = {n};")
     out.append(f"    static constexpr bool IS_BN = {'true' if twist == 'D' else 'false'};")
@@ -74,7 +78,7 @@ def emit(name, p, r, xi, b, twist, n, extra):
     out.append(f"        constexpr uint32_t v[{n}] = {arr(limbs(p, n))};")
     out.append("        return v[i];")
     out.append("    }")
-    for t in ("P", "R1", "R2", "HALF", "B1", "B1X3", "B2", "B2X3", "PM2"):
+    for t in ["P", "R1", "R2", "HALF", "B1", "B1X3", "B2", "B2X3", "PM2", "PP1D4", "PM1D2"] + [c for c, _ in extra_consts]:
         out.append(f"    HD static const uint32_t* {t}() {{ return {U}_{t}; }}")
     for t in ("GAMMA1", "GAMMA2", "GAMMA3"):
         out.append(f"    HD static const uint32_t* {t}(int k) {{ return {U}_{t}[k]; }}")
@@ -108,6 +112,16 @@ def main():
         f"    static constexpr unsigned long long C_LO = 0x{c & (2**64 - 1):x}ull, C_HI = 0x{c >> 64:x}ull;  // (|x|+1)^2/3",
         "    static constexpr int FP_BYTES = 48;",
     ]
+    # Fouque-Tibouchi / SvdW hash constants and the G1 generator (curves/bls12_381.go:333-346)
+    bl_consts = [
+        ("FT_SQRT_NEG3", 1586958781458431025242759403266842894121773480562120986020912974854563298150952611241517463240701),
+        ("FT_Z", 793479390729215512621379701633421447060886740281060493010456487427281649075476305620758731620350),
+        ("FT_ROOT1", 248294325734266649657405162895821171812231848760181225578082735178502750823719347628762635478508544819911854747095),
+        ("FT_ROOT2", 3754115229487400743760384662840082984744650971178826659753975400945528899667118516813924993650507119217982417812692),
+        ("G1X", 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb),
+        ("G1Y", 0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1),
+        ("TWO376", 1 << 376),
+    ]
     hdr = [
         "// GENERATED by tools/gen_constants.py -- do not edit.",
         "// Montgomery constants, R = 2^(32 N); 32-bit little-endian limbs.",
@@ -115,8 +129,8 @@ def main():
         "#include <cstdint>",
         '#include "arith.cuh"',
         "namespace bgls {",
-        emit("BN254", bn_p, bn_r, (9, 1), 3, "D", 8, bn_extra),
-        emit("BLS381", bl_p, bl_r, (1, 1), 4, "M", 12, bl_extra),
+        emit("BN254", bn_p, bn_r, (9, 1), 3, "D", 8, bn_extra, [("TWO248", 1 << 248)]),
+        emit("BLS381", bl_p, bl_r, (1, 1), 4, "M", 12, bl_extra, bl_consts),
         "}  // namespace bgls",
         "",
     ]
