@@ -205,8 +205,8 @@ using namespace bgls;
 
 // device copies of the machine tables of one curve
 struct MachDev {
-    MachTables m{}, f{};
-    const uint16_t *miller = nullptr, *mul_ab = nullptr, *mul_ba = nullptr, *import_a = nullptr;
+    MachTables m{}, f{}, p{};   // 16-lane product file, final-exponentiation file, pipelined 32-lane Miller file
+    const uint16_t *miller = nullptr, *mul_ab = nullptr, *mul_ba = nullptr, *import_a = nullptr, *miller_p = nullptr;
     const uint16_t *finalexp = nullptr, *export_ = nullptr;
     void* blob = nullptr;
 };
@@ -215,7 +215,9 @@ struct bgls_ctx {
     MachDev mach[2];
     bool thread_engine = false;  // BGLS_ENGINE=thread: thread-per-pair kernels only
     bool machine_only = false;   // BGLS_ENGINE=machine: dot-product machine at every size (no hybrid)
+    bool miller16 = false;       // BGLS_MILLER=m16: 16-lane Miller program (two pairings per warp) instead of the pipelined one
     int device = 0;
+    int sms = 148;
     cudaStream_t stream = nullptr;
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -363,7 +365,7 @@ int batch_dev_thread(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g
 }
 
 // ---- machine tables upload
-template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, MachDev& d) {
+template <class M, class MT, class F, class FT, class P, class PT> int upload_mach(bgls_ctx* ctx, MachDev& d) {
     struct Part { const void* src; size_t bytes; const void** dst; };
     const Part parts[] = {
         {MT::consts(), sizeof(uint32_t) * M::NCONST * M::L, (const void**)&d.m.consts},
@@ -378,6 +380,10 @@ template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, M
         {MT::prog_IMPORT_A(), sizeof(uint16_t) * M::IMPORT_A_LEN, (const void**)&d.import_a},
         {FT::prog_FINALEXP(), sizeof(uint16_t) * F::FINALEXP_LEN, (const void**)&d.finalexp},
         {FT::prog_EXPORT(), sizeof(uint16_t) * F::EXPORT_LEN, (const void**)&d.export_},
+        {PT::consts(), sizeof(uint32_t) * P::NCONST * P::L, (const void**)&d.p.consts},
+        {PT::hdr(), sizeof(uint32_t) * P::NPHASE, (const void**)&d.p.hdr},
+        {PT::rec(), sizeof(uint16_t) * P::NPHASE * P::LANES * P::REC, (const void**)&d.p.rec},
+        {PT::prog_MILLER(), sizeof(uint16_t) * P::MILLER_LEN, (const void**)&d.miller_p},
     };
     size_t total = 0;
     for (const Part& p : parts) total += align_up(p.bytes);
@@ -393,6 +399,7 @@ template <class M, class MT, class F, class FT> int upload_mach(bgls_ctx* ctx, M
     CU(cudaFuncSetAttribute(k_mach_reduce<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_import<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(1)));
+    CU(cudaFuncSetAttribute(k_mach_miller32<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<P>(MP_MAXW)));
     return BGLS_OK;
 }
 
@@ -401,9 +408,22 @@ constexpr size_t MHYBRID = 16384;  // pairs: above this the thread-per-pair Mill
 constexpr size_t MSMALL = 0;  // GPW=1 threshold: measured slower on B200 (1.55 ms vs 1.19 ms at 1025 pairs: the IMAD pipe is
                               // charged per warp instruction, so half-empty warps double the pipe work); kept for experiments
 
+template <class M> struct PFile;
+template <> struct PFile<mtab::BN254_M> { using type = mtab::BN254_MP; };
+template <> struct PFile<mtab::BLS381_M> { using type = mtab::BLS381_MP; };
+
 template <class M>
 void launch_miller(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, uint32_t* vals, cudaStream_t s) {
     if (n == 0) return;
+    if (!ctx->miller16) {
+        // one pairing per warp; the block size spreads the pairs over all SMs (small products) up to 16 warps per SM
+        using P = typename PFile<M>::type;
+        size_t wpb = (n + ctx->sms - 1) / ctx->sms;
+        if (wpb > (size_t)MP_MAXW) wpb = MP_MAXW;
+        k_mach_miller32<P><<<(unsigned)((n + wpb - 1) / wpb), (unsigned)wpb * 32, mach_smem_bytes<P>((int)wpb), s>>>(d.p, d.miller_p, P::MILLER_LEN, d_g1, d_g2, n, vals);
+        ctx->launches++;
+        return;
+    }
     if (n <= MSMALL)
         k_mach_miller<M, 1><<<(unsigned)((n + MWPB - 1) / MWPB), MWPB * 32, mach_smem_bytes<M>(MWPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, vals);
     else
@@ -446,7 +466,7 @@ int mach_pairing(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uin
     uint32_t* res;
     int rc = mach_tree<M>(ctx, d, buf0, buf1, n, &res, s);
     if (rc) return rc;
-    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
+    k_mach_finish<F, M><<<1, MFIN_THREADS, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
                                                            res, 1, d_out, d_flag, nullptr);
     ctx->launches++;
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
@@ -466,7 +486,7 @@ int mach_finish_bytes(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_partials
     uint32_t* res;
     int rc = mach_tree<M>(ctx, d, buf0, buf1, k, &res, s);
     if (rc) return rc;
-    k_mach_finish<F, M><<<1, 32, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
+    k_mach_finish<F, M><<<1, MFIN_THREADS, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
                                                            res, 1, d_out, d_flag, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -480,7 +500,7 @@ int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8
     uint32_t* buf1 = (uint32_t*)((char*)work + align_up((total + 2) * mach_val_bytes<M>()));
     launch_miller<M>(ctx, d, d_g1, d_g2, total, buf0, s);
     k_mach_reduce<M><<<(unsigned)((nbatch + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, buf0, total, 0, d_off, nbatch, buf1);
-    k_mach_finish<F, M><<<(unsigned)nbatch, 32, mach_smem_bytes<F>(1), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
+    k_mach_finish<F, M><<<(unsigned)nbatch, MFIN_THREADS, mach_smem_bytes<F>(1), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
     ctx->launches += 2;
     CU(cudaGetLastError());
     return BGLS_OK;
@@ -563,8 +583,12 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     const char* eng = getenv("BGLS_ENGINE");
     ctx->thread_engine = eng && std::string(eng) == "thread";
     ctx->machine_only = eng && std::string(eng) == "machine";
-    int rc = upload_mach<mtab::BN254_M, mtab::BN254_M_T, mtab::BN254_F, mtab::BN254_F_T>(ctx, ctx->mach[0]);
-    if (!rc) rc = upload_mach<mtab::BLS381_M, mtab::BLS381_M_T, mtab::BLS381_F, mtab::BLS381_F_T>(ctx, ctx->mach[1]);
+    const char* mil = getenv("BGLS_MILLER");
+    ctx->miller16 = mil && std::string(mil) == "m16";
+    cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->sms <= 0) ctx->sms = 148;
+    int rc = upload_mach<mtab::BN254_M, mtab::BN254_M_T, mtab::BN254_F, mtab::BN254_F_T, mtab::BN254_MP, mtab::BN254_MP_T>(ctx, ctx->mach[0]);
+    if (!rc) rc = upload_mach<mtab::BLS381_M, mtab::BLS381_M_T, mtab::BLS381_F, mtab::BLS381_F_T, mtab::BLS381_MP, mtab::BLS381_MP_T>(ctx, ctx->mach[1]);
     if (rc) {
         bgls_ctx_destroy(ctx);
         return rc;

@@ -1,9 +1,12 @@
 // Interpreter of the warp-cooperative "dot-product machine" (schedules: tools/gen_machine.py,
 // tables: machine_tables.cuh).
 //
-// A group of 16 lanes owns one pairing.  All state is a file of Fp slots in shared memory, stored
-// word-major (limb i of slot s at gs[i*NSG + s]) so that lanes reading different slots hit
-// different banks.  Fp elements are L limbs of 28 bits (unsaturated), Montgomery form with
+// A group of 16 or 32 lanes owns one pairing.  All state is a file of Fp slots in shared memory, stored
+// word-major (limb i of slot s at gs[i*NS + s]) so that lanes reading different slots hit different
+// banks; the file holds the NSG group slots followed by a private copy of the NCONST constants, so
+// every operand is addressed the same way (one base register + immediate offsets).
+// Signed slot files (M::SIGNED): bit 15 of a DOT term's first operand negates that operand and the
+// columns are signed; the phase header carries K so that K p is added to the reduced value (never negative).  Fp elements are L limbs of 28 bits (unsaturated), Montgomery form with
 // R = 2^(28 L); values are only kept bounded (bounds proven statically by the generator).
 //   DOT task:  dst = MontRed( sum_t a_t * b_t )   -- products accumulate carry-free in 64-bit columns
 //              with full-rate IMAD.WIDE.U32 (measured 2x the throughput of the carry-chained form),
@@ -23,32 +26,36 @@ constexpr uint32_t MIDLE = 0xFFFFu;
 //   [0] dst, [1..TM] a slots (LIN: sources), [1+TM..2TM] b slots (LIN: coefficient words)
 
 template <class M> struct MachView {
-    uint32_t* gs;        // group slot file, word-major, NSG slots
-    const uint32_t* cs;  // block-shared constant slots, word-major, NCONST slots
+    uint32_t* gs;        // group slot file, word-major, NS = NSG + NCONST slots
 };
 
 template <class M> HD void mach_load(uint32_t* v, const MachView<M>& mv, uint32_t s) {
-    const bool isg = s < (uint32_t)M::NSG;
-    const uint32_t* base = isg ? mv.gs + s : mv.cs + (s - M::NSG);
-    const int stride = isg ? M::NSG : M::NCONST;
+    const uint32_t* base = mv.gs + s;
 #pragma unroll
-    for (int i = 0; i < M::L; i++) v[i] = base[i * stride];
+    for (int i = 0; i < M::L; i++) v[i] = base[i * M::NS];
 }
 template <class M> HD void mach_store(const MachView<M>& mv, uint32_t s, const uint32_t* v) {
 #pragma unroll
-    for (int i = 0; i < M::L; i++) mv.gs[i * M::NSG + s] = v[i];
+    for (int i = 0; i < M::L; i++) mv.gs[i * M::NS + s] = v[i];
+}
+// copies the constants of the slot file into the tail of one group file
+template <class M> HD void mach_fill_consts(uint32_t* gs, const uint32_t* consts /* [NCONST][L] */, int first = 0, int step = 1) {
+    for (int idx = first; idx < M::NCONST * M::L; idx += step) {
+        const int c = idx / M::L, i = idx % M::L;
+        gs[i * M::NS + M::NSG + c] = consts[idx];
+    }
 }
 
 // Montgomery reduction of 2L 64-bit columns (radix 2^W) to L normalised limbs: (T + m p) / R
-template <class M> HD void mach_montred(uint32_t* out, unsigned long long* acc) {
+template <class M, class ACC> HD void mach_montred(uint32_t* out, ACC* acc) {
     constexpr int L = M::L, W = M::W;
     constexpr uint32_t MASK = (1u << W) - 1;
 #pragma unroll
     for (int i = 0; i < L; i++) {
         const uint32_t m = ((uint32_t)acc[i] * M::N0) & MASK;
 #pragma unroll
-        for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)m * M::p(j);
-        acc[i + 1] += acc[i] >> W;
+        for (int j = 0; j < L; j++) acc[i + j] += (ACC)((unsigned long long)m * M::p(j));
+        acc[i + 1] += acc[i] >> W;   // exact: the low W bits are zero (arithmetic shift for signed columns)
     }
 #pragma unroll
     for (int k = L; k < 2 * L - 1; k++) {
@@ -60,27 +67,56 @@ template <class M> HD void mach_montred(uint32_t* out, unsigned long long* acc) 
 
 // one DOT task; rec: lane record, T: number of terms of the phase (uniform over the warp).
 // The operands of term t+1 are fetched while the L*L multiply-accumulates of term t issue.
-template <class M> HD void mach_dot(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t* out) {
+template <class M> HD void mach_dot(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t K, uint32_t* out) {
     constexpr int L = M::L;
-    unsigned long long acc[2 * L];
+    if constexpr (M::SIGNED) {
+        long long acc[2 * L];
 #pragma unroll
-    for (int i = 0; i < 2 * L; i++) acc[i] = 0;
-    uint32_t a[L], b[L];
-    mach_load<M>(a, mv, rec[1]);
-    mach_load<M>(b, mv, rec[1 + M::TM]);
-    for (int t = 0; t < T; t++) {
-        uint32_t na[L], nb[L];
-        const int tn = t + 1 < T ? t + 1 : t;
-        mach_load<M>(na, mv, rec[1 + tn]);
-        mach_load<M>(nb, mv, rec[1 + M::TM + tn]);
+        for (int i = 0; i < L; i++) { acc[i] = 0; acc[L + i] = (long long)((unsigned long long)K * M::p(i)); }
+        uint32_t a[L], b[L];
+        uint32_t ra = rec[1];
+        mach_load<M>(a, mv, ra & 0x7FFFu);
+        mach_load<M>(b, mv, rec[1 + M::TM]);
+        for (int t = 0; t < T; t++) {
+            uint32_t na[L], nb[L];
+            const int tn = t + 1 < T ? t + 1 : t;
+            const uint32_t rn = rec[1 + tn];
+            mach_load<M>(na, mv, rn & 0x7FFFu);
+            mach_load<M>(nb, mv, rec[1 + M::TM + tn]);
+            const bool neg = (ra & 0x8000u) != 0;
+            int sa[L];
 #pragma unroll
-        for (int i = 0; i < L; i++)
+            for (int i = 0; i < L; i++) sa[i] = neg ? -(int)a[i] : (int)a[i];
 #pragma unroll
-            for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)a[i] * b[j];
+            for (int i = 0; i < L; i++)
 #pragma unroll
-        for (int i = 0; i < L; i++) { a[i] = na[i]; b[i] = nb[i]; }
+                for (int j = 0; j < L; j++) acc[i + j] += (long long)sa[i] * (long long)(int)b[j];
+#pragma unroll
+            for (int i = 0; i < L; i++) { a[i] = na[i]; b[i] = nb[i]; }
+            ra = rn;
+        }
+        mach_montred<M, long long>(out, acc);
+    } else {
+        unsigned long long acc[2 * L];
+#pragma unroll
+        for (int i = 0; i < 2 * L; i++) acc[i] = 0;
+        uint32_t a[L], b[L];
+        mach_load<M>(a, mv, rec[1]);
+        mach_load<M>(b, mv, rec[1 + M::TM]);
+        for (int t = 0; t < T; t++) {
+            uint32_t na[L], nb[L];
+            const int tn = t + 1 < T ? t + 1 : t;
+            mach_load<M>(na, mv, rec[1 + tn]);
+            mach_load<M>(nb, mv, rec[1 + M::TM + tn]);
+#pragma unroll
+            for (int i = 0; i < L; i++)
+#pragma unroll
+                for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)a[i] * b[j];
+#pragma unroll
+            for (int i = 0; i < L; i++) { a[i] = na[i]; b[i] = nb[i]; }
+        }
+        mach_montred<M, unsigned long long>(out, acc);
     }
-    mach_montred<M>(out, acc);
 }
 
 template <class M> HD void mach_lin(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t* out) {
@@ -299,7 +335,7 @@ template <class M> HD void mach_phase_lane(const MachView<M>& mv, const MachTabl
         }
         return;
     }
-    if (kind == 0) mach_dot<M>(mv, rec, T, out);
+    if (kind == 0) mach_dot<M>(mv, rec, T, h >> 24, out);
     else mach_lin<M>(mv, rec, T, out);
     if (rec[0] != MIDLE) mach_store<M>(mv, rec[0], out);
 }

@@ -13,36 +13,40 @@
 namespace bgls {
 
 constexpr int MWPB = 4;                 // warps per block
+constexpr int MP_MAXW = 16;             // k_mach_miller32: pairings (warps) per block, at most
+constexpr int MFIN_THREADS = 256;       // k_mach_finish: one working warp, the others only stage the tables
 constexpr int MGPB = MWPB * 2;          // groups per block
 
 // shared memory layout of every machine kernel (32-bit words):
-//   [ constants (word-major) | phase headers | phase records (u16 x 26 x 16 per phase) | group slot files ]
-// Keeping the schedule tables on chip removes every global load from the phase loop.
+//   [ phase headers | phase records (u16 x REC x LANES per phase) | group slot files (NS slots each) ]
+// Keeping the schedule tables on chip removes every global load from the phase loop; every group file
+// ends with its own copy of the constants so that all operands share one addressing form.
 template <class M> __host__ __device__ constexpr size_t mach_tab_words() {
-    return (size_t)M::NCONST * M::L + M::NPHASE + ((size_t)M::NPHASE * M::LANES * M::REC + 1) / 2;
+    return (size_t)M::NPHASE + ((size_t)M::NPHASE * M::LANES * M::REC + 1) / 2;
 }
 template <class M> constexpr size_t mach_smem_bytes(int groups) {
-    return (mach_tab_words<M>() + (size_t)groups * M::NSG * M::L) * sizeof(uint32_t);
+    return (mach_tab_words<M>() + (size_t)groups * M::NS * M::L) * sizeof(uint32_t);
 }
 
-// copies the tables into shared memory; returns the group area and rewrites `tb` to the on-chip copies
-template <class M> __device__ __forceinline__ uint32_t* mach_stage_tables(uint32_t* sm, MachTables& tb) {
-    uint32_t* cs = sm;
-    uint32_t* hdr = cs + M::NCONST * M::L;
+// copies the tables into shared memory and the constants into the `groups` group files; returns the group
+// area and rewrites `tb` to the on-chip copies
+template <class M> __device__ __forceinline__ uint32_t* mach_stage_tables(uint32_t* sm, MachTables& tb, int groups) {
+    uint32_t* hdr = sm;
     uint32_t* rec = hdr + M::NPHASE;
-    for (int idx = threadIdx.x; idx < M::NCONST * M::L; idx += blockDim.x) {
-        const int c = idx / M::L, i = idx % M::L;
-        cs[i * M::NCONST + c] = tb.consts[idx];
-    }
+    uint32_t* gbase = sm + mach_tab_words<M>();
     for (int idx = threadIdx.x; idx < M::NPHASE; idx += blockDim.x) hdr[idx] = tb.hdr[idx];
-    const uint32_t* rsrc = (const uint32_t*)tb.rec;   // NPHASE*16*26 u16 = even number of u16
+    const uint32_t* rsrc = (const uint32_t*)tb.rec;   // NPHASE*LANES*REC u16 = even number of u16
     constexpr int RW = M::NPHASE * M::LANES * M::REC / 2;
     for (int idx = threadIdx.x; idx < RW; idx += blockDim.x) rec[idx] = rsrc[idx];
+    constexpr int CW = M::NCONST * M::L;
+    for (int idx = threadIdx.x; idx < groups * CW; idx += blockDim.x) {
+        const int g = idx / CW, r = idx % CW, c = r / M::L, i = r % M::L;
+        gbase[(size_t)g * M::NS * M::L + i * M::NS + M::NSG + c] = tb.consts[r];
+    }
     __syncthreads();
-    tb.consts = cs;
     tb.hdr = hdr;
     tb.rec = (const uint16_t*)rec;
-    return sm + mach_tab_words<M>();
+    return gbase;
 }
 
 template <class M> __device__ __forceinline__ void mach_run(const MachView<M>& mv, const MachTables& tb,
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const 
     extern __shared__ uint32_t sm[];
     constexpr int L = M::L, FB = M::FP_BYTES;
     constexpr int GPB = MWPB * GPW;  // groups per block
-    uint32_t* gbase = mach_stage_tables<M>(sm, tb);
+    uint32_t* gbase = mach_stage_tables<M>(sm, tb, GPB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (GPW == 1 && lane >= MG) return;
     const int g = GPW == 2 ? (threadIdx.x >> 4) : warp, gl = lane & 15;
@@ -77,8 +81,7 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const 
     const size_t warp_first = (size_t)blockIdx.x * GPB + (GPW == 2 ? (g & ~1) : g);
     if (warp_first >= n) return;  // whole warp idle
     MachView<M> mv;
-    mv.gs = gbase + (size_t)g * M::NSG * L;
-    mv.cs = tb.consts;
+    mv.gs = gbase + (size_t)g * M::NS * L;
     const bool active = pair < n;
     // inputs: lanes 0..5 of the group convert one coordinate each
     bool zero = true, flag = false;
@@ -109,6 +112,51 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const 
     }
 }
 
+// ---------------------------------------------------------------- K1p
+// Latency path: one pairing per warp running the pipelined program of the signed 32-lane slot file P
+// (tools/gen_machine.py: build_miller_p).  blockDim.x / 32 pairings per block, chosen by the host so that the
+// grid covers all SMs with as many resident warps per SM sub-partition as the product offers.
+template <class P>
+__global__ void __launch_bounds__(512) k_mach_miller32(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+                                                      const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                      size_t n, uint32_t* __restrict__ vals) {
+    extern __shared__ uint32_t sm[];
+    constexpr int L = P::L, FB = P::FP_BYTES;
+    static_assert(P::LANES == 32, "one warp per pairing");
+    const int wpb = blockDim.x >> 5;
+    uint32_t* gbase = mach_stage_tables<P>(sm, tb, wpb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t pair = (size_t)blockIdx.x * wpb + warp;
+    if (pair >= n) return;
+    MachView<P> mv;
+    mv.gs = gbase + (size_t)warp * P::NS * L;
+    bool zero = true, flag = false;
+    if (lane < 6) {   // lanes 0..5 convert one coordinate each
+        const uint8_t* src = lane < 2 ? g1 + pair * 2 * FB + lane * FB : g2 + pair * 4 * FB + (lane - 2) * FB;
+        const int slot = lane == 0 ? P::IN_XP : lane == 1 ? P::IN_YP : lane == 2 ? P::IN_XQY : lane == 3 ? P::IN_XQX : lane == 4 ? P::IN_YQY : P::IN_YQX;
+        uint32_t v[L];
+        mach_limbs_from_be<P>(v, src);
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < L; i++) any |= v[i];
+        zero = any == 0;
+        flag = FB == 48 && (lane == 0 || lane == 2) && (src[0] & 0x40);
+        mach_store<P>(mv, slot, v);
+    }
+    const unsigned zb = __ballot_sync(0xFFFFFFFFu, zero) & 0x3Fu;
+    const unsigned fb = __ballot_sync(0xFFFFFFFFu, flag) & 0x3Fu;
+    const bool inf = ((zb & 0x3u) == 0x3u) || ((zb & 0x3Cu) == 0x3Cu) || (fb & 0x5u);
+    __syncwarp();
+    mach_run<P>(mv, tb, prog, plen, lane);
+    if (lane < 12) {
+        uint32_t v[L];
+        mach_load<P>(v, mv, inf ? (lane == 0 ? P::ONE : P::ZERO) : P::FA0 + lane);
+        uint32_t* o = vals + (pair * 12 + lane) * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) o[i] = v[i];
+    }
+}
+
 // ---------------------------------------------------------------- K2
 // output g = product of inputs [lo, hi): lo/hi from `seg` (nout+1 offsets) when given, else chunks of `chunk`
 template <class M>
@@ -118,14 +166,13 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_reduce(MachTables tb, const 
                                                           size_t n_out, uint32_t* __restrict__ out) {
     extern __shared__ uint32_t sm[];
     constexpr int L = M::L;
-    uint32_t* gbase = mach_stage_tables<M>(sm, tb);
+    uint32_t* gbase = mach_stage_tables<M>(sm, tb, MGPB);
     const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
     const size_t o = (size_t)blockIdx.x * MGPB + g;
     const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
     if (warp_first >= n_out) return;
     MachView<M> mv;
-    mv.gs = gbase + (size_t)g * M::NSG * L;
-    mv.cs = tb.consts;
+    mv.gs = gbase + (size_t)g * M::NS * L;
     const bool active = o < n_out;
     size_t lo = 0, hi = 0;
     if (active) {
@@ -178,19 +225,19 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_reduce(MachTables tb, const 
 // one 32-lane group (one warp, one block) per value: FINALEXP (or EXPORT) then canonical wire bytes;
 // flags[o] = 1 iff the result is 1.  The F slot file splits every long dot over two lanes.
 template <class F, class MIN>
-__global__ void __launch_bounds__(32) k_mach_finish(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+__global__ void __launch_bounds__(MFIN_THREADS) k_mach_finish(MachTables tb, const uint16_t* __restrict__ prog, int plen,
                                                    const uint32_t* __restrict__ in, size_t n, uint8_t* __restrict__ out_gt,
                                                    int* __restrict__ flags32, uint8_t* __restrict__ flags8) {
     extern __shared__ uint32_t sm[];
     constexpr int L = F::L, FB = F::FP_BYTES;
     static_assert(F::L == MIN::L, "limb layout mismatch between slot files");
     static_assert(F::LANES == 32, "the final-exponentiation slot file is scheduled for 32-lane groups");
-    uint32_t* gbase = mach_stage_tables<F>(sm, tb);
+    uint32_t* gbase = mach_stage_tables<F>(sm, tb, 1);
+    if (threadIdx.x >= 32) return;   // the extra warps only help staging the tables
     const int gl = threadIdx.x;
     const size_t o = blockIdx.x;
     MachView<F> mv;
     mv.gs = gbase;
-    mv.cs = tb.consts;
     if (gl < 12) {
         uint32_t v[L];
         const uint32_t* src = in + (o * 12 + gl) * L;
@@ -230,14 +277,13 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_import(MachTables tb, const 
                                                           const uint8_t* __restrict__ in, size_t n, uint32_t* __restrict__ vals) {
     extern __shared__ uint32_t sm[];
     constexpr int L = M::L, FB = M::FP_BYTES;
-    uint32_t* gbase = mach_stage_tables<M>(sm, tb);
+    uint32_t* gbase = mach_stage_tables<M>(sm, tb, MGPB);
     const int g = threadIdx.x >> 4, gl = threadIdx.x & 15;
     const size_t o = (size_t)blockIdx.x * MGPB + g;
     const size_t warp_first = (size_t)blockIdx.x * MGPB + (g & ~1);
     if (warp_first >= n) return;
     MachView<M> mv;
-    mv.gs = gbase + (size_t)g * M::NSG * L;
-    mv.cs = tb.consts;
+    mv.gs = gbase + (size_t)g * M::NS * L;
     const bool active = o < n;
     if (gl < 12) {
         uint32_t v[L];

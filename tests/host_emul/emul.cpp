@@ -62,14 +62,12 @@ void emu_fpops(int curve, const uint8_t* a, const uint8_t* b, uint8_t* out) {
 #include "../../bgls_b200/csrc/machine_tables.cuh"
 
 template <class M, class T> struct HostMach {
-    std::vector<uint32_t> gs, cs;
+    std::vector<uint32_t> gs;
     MachView<M> mv;
     MachTables tb;
-    HostMach() : gs((size_t)M::NSG * M::L, 0), cs((size_t)M::NCONST * M::L, 0) {
-        for (int c = 0; c < M::NCONST; c++)
-            for (int i = 0; i < M::L; i++) cs[(size_t)i * M::NCONST + c] = T::consts()[c * M::L + i];
+    HostMach() : gs((size_t)M::NS * M::L, 0) {
+        mach_fill_consts<M>(gs.data(), T::consts());
         mv.gs = gs.data();
-        mv.cs = cs.data();
         tb.consts = T::consts();
         tb.hdr = T::hdr();
         tb.rec = T::rec();
@@ -84,7 +82,7 @@ template <class M, class T> struct HostMach {
                 const uint16_t* rec = tb.rec + ((size_t)ph * M::LANES + lane) * M::REC;
                 if ((h & 0xFF) == 2) {
                     if (rec[0] != MIDLE) { uint32_t in[M::L]; mach_load<M>(in, mv, rec[1]); mach_inv<M>(outs[lane], in); }
-                } else if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, Tn, outs[lane]);
+                } else if ((h & 0xFF) == 0) mach_dot<M>(mv, rec, Tn, h >> 24, outs[lane]);
                 else mach_lin<M>(mv, rec, Tn, outs[lane]);
             }
             for (int lane = 0; lane < M::LANES; lane++) {  // deferred stores: a phase must be hazard-free
@@ -97,16 +95,18 @@ template <class M, class T> struct HostMach {
     void get(int s, uint32_t* v) { mach_load<M>(v, mv, s); }
 };
 
-template <class MM, class MT, class FM, class FT>
+// PM/PT: slot file that runs the Miller program (the 16-lane M file or the pipelined 32-lane P file)
+template <class MM, class MT, class FM, class FT, class PM = MM, class PT = MT>
 static int mach_pairing(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final, uint32_t* dbg_f) {
     constexpr int L = MM::L, FB = MM::FP_BYTES;
+    static_assert(PM::L == MM::L && PM::W == MM::W, "limb layouts must agree");
     HostMach<MM, MT> acc;   // accumulator group: product tree through MUL_AB / MUL_BA
     bool have = false, in_a = true;
     uint32_t one[L], zero[L];
     acc.get(MM::ONE, one);
     acc.get(MM::ZERO, zero);
     for (size_t i = 0; i < n; i++) {
-        HostMach<MM, MT> m;
+        HostMach<PM, PT> m;
         const uint8_t* p1 = g1 + i * 2 * FB;
         const uint8_t* p2 = g2 + i * 4 * FB;
         bool inf = bytes_all_zero(p1, 2 * FB) || bytes_all_zero(p2, 4 * FB) || (FB == 48 && ((p1[0] & 0x40) || (p2[0] & 0x40)));
@@ -115,14 +115,14 @@ static int mach_pairing(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t*
             for (int k = 0; k < 12; k++) memcpy(f[k], k == 0 ? one : zero, sizeof(one));
         } else {
             uint32_t v[L];
-            mach_limbs_from_be<MM>(v, p1); m.set(MM::IN_XP, v);
-            mach_limbs_from_be<MM>(v, p1 + FB); m.set(MM::IN_YP, v);
-            mach_limbs_from_be<MM>(v, p2); m.set(MM::IN_XQY, v);
-            mach_limbs_from_be<MM>(v, p2 + FB); m.set(MM::IN_XQX, v);
-            mach_limbs_from_be<MM>(v, p2 + 2 * FB); m.set(MM::IN_YQY, v);
-            mach_limbs_from_be<MM>(v, p2 + 3 * FB); m.set(MM::IN_YQX, v);
-            m.run(MT::prog_MILLER(), MM::MILLER_LEN);
-            for (int k = 0; k < 12; k++) m.get(MM::FA0 + k, f[k]);
+            mach_limbs_from_be<PM>(v, p1); m.set(PM::IN_XP, v);
+            mach_limbs_from_be<PM>(v, p1 + FB); m.set(PM::IN_YP, v);
+            mach_limbs_from_be<PM>(v, p2); m.set(PM::IN_XQY, v);
+            mach_limbs_from_be<PM>(v, p2 + FB); m.set(PM::IN_XQX, v);
+            mach_limbs_from_be<PM>(v, p2 + 2 * FB); m.set(PM::IN_YQY, v);
+            mach_limbs_from_be<PM>(v, p2 + 3 * FB); m.set(PM::IN_YQX, v);
+            m.run(PT::prog_MILLER(), PM::MILLER_LEN);
+            for (int k = 0; k < 12; k++) m.get(PM::FA0 + k, f[k]);
         }
         if (dbg_f && i == 0) memcpy(dbg_f, f, sizeof(f));
         if (!have) {
@@ -166,6 +166,12 @@ extern "C" int emu_mach_pairing_product(int curve, const uint8_t* g1, const uint
     using namespace mtab;
     if (curve == 0) return mach_pairing<BN254_M, BN254_M_T, BN254_F, BN254_F_T>(g1, g2, n, out, do_final, dbg_f);
     return mach_pairing<BLS381_M, BLS381_M_T, BLS381_F, BLS381_F_T>(g1, g2, n, out, do_final, dbg_f);
+}
+// same pipeline with the Miller loops run by the pipelined 32-lane program (slot file P)
+extern "C" int emu_mach_pairing_product_p(int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final) {
+    using namespace mtab;
+    if (curve == 0) return mach_pairing<BN254_M, BN254_M_T, BN254_F, BN254_F_T, BN254_MP, BN254_MP_T>(g1, g2, n, out, do_final, nullptr);
+    return mach_pairing<BLS381_M, BLS381_M_T, BLS381_F, BLS381_F_T, BLS381_MP, BLS381_MP_T>(g1, g2, n, out, do_final, nullptr);
 }
 
 // ============================================================ hash-to-G1 (host emulation of the device functions)

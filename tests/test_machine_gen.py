@@ -43,6 +43,15 @@ def test_programs_against_oracle(built, cfg, c):
     f = [(sim.get(FA[k][0]) * Rinv % cfg.p, sim.get(FA[k][1]) * Rinv % cfg.p) for k in range(6)]
     want = c.pair(P, Q)
     assert c.final_exp(f) == want
+    # the pipelined 32-lane program (slot file P, signed terms) computes the same pairing
+    simp = GM.Sim(gens["P"])
+    for k, v in (("xP", P[0]), ("yP", P[1]), ("xQ.x", Q[0][0]), ("xQ.y", Q[0][1]), ("yQ.x", Q[1][0]), ("yQ.y", Q[1][1])):
+        simp.set(io["p_miller_in"][k], v)
+    simp.run("MILLER")
+    PFA = io["P_FA"]
+    fp_ = [(simp.get(PFA[k][0]) * Rinv % cfg.p, simp.get(PFA[k][1]) * Rinv % cfg.p) for k in range(6)]
+    assert c.final_exp(fp_) == want
+    assert simp.maxv < cfg.R
     simf = GM.Sim(gf)
     for k in range(6):
         for cc in range(2):

@@ -110,9 +110,15 @@ class Phase:
 class Gen:
     """Builds phases/programs for one curve and tracks static value bounds."""
 
-    def __init__(self, cfg: Cfg, lanes=G, tm=MAXT, split=False):
+    def __init__(self, cfg: Cfg, lanes=G, tm=MAXT, split=False, signed=False):
         self.cfg = cfg
         self.lanes, self.tm, self.split = lanes, tm, split   # lanes per group, max terms per DOT record, split long dots
+        # signed slot files: a DOT term may carry a minus sign (the interpreter negates the limbs of its first
+        # operand and accumulates in signed 64-bit columns); the phase header holds an offset K so that K p R
+        # dominates the negative part, i.e. the reduced value (T + m p)/R + K p is never negative.
+        self.signed = signed
+        if signed:
+            assert (tm + 1) * cfg.L * (1 << (2 * cfg.W)) < (1 << 63), "signed 64-bit columns would overflow"
         self.gslots = {}       # name -> index (per-group slot)
         self._nslots, self._pool, self._pools, self._pool_used = 0, None, {}, {}
         self.cslots = {}       # name -> index (block-shared constant slot)
@@ -230,11 +236,19 @@ class Gen:
                 new_ub[dst] = cfg.p - 1
                 continue
             if phase.kind == "DOT":
-                s = 0
-                for a, b in terms:
+                s, neg = 0, 0
+                for t in terms:
+                    a, b = t[0], t[1]
                     assert self.ub.get(a) is not None and self.ub.get(b) is not None, ("unbounded DOT operand", a, b)
-                    s += self.ub[a] * self.ub[b]
-                ub = s // cfg.R + cfg.p
+                    if len(t) > 2 and t[2] < 0:
+                        assert self.signed, "negative DOT term in an unsigned slot file"
+                        neg += self.ub[a] * self.ub[b]
+                    else:
+                        s += self.ub[a] * self.ub[b]
+                if neg:
+                    need = -(-(neg + neg // 2) // (cfg.p * cfg.R))   # 1.5x margin: phases are re-used
+                    phase.K = max(getattr(phase, "K", 0), need)
+                ub = s // cfg.R + cfg.p    # + K p, added below once the phase's K is known
             else:
                 ub = 0
                 for slot, coef, K in terms:
@@ -249,9 +263,16 @@ class Gen:
                         ub += -coef * K * cfg.p
             assert ub < cfg.R, ("value bound exceeds R", ub.bit_length())
             new_ub[dst] = ub
+        if phase.kind == "DOT" and getattr(phase, "K", 0):
+            assert phase.K < 256
+            for dst in new_ub:
+                new_ub[dst] += phase.K * cfg.p
+                assert new_ub[dst] < cfg.R
         sig = (phase.kind, tuple((d, tuple(t)) for d, t in phase.tasks))
         if sig in self.cache:
             pid = self.cache[sig]   # bounds of every execution are re-verified by verify_program()
+            if getattr(phase, "K", 0) > getattr(self.phases[pid], "K", 0):
+                self.phases[pid].K = phase.K
         else:
             pid = len(self.phases)
             self.phases.append(phase)
@@ -277,11 +298,17 @@ class Gen:
                     new[dst] = cfg.p - 1
                     continue
                 if ph.kind == "DOT":
-                    acc = 0
-                    for a, b in terms:
+                    acc, neg = 0, 0
+                    for t in terms:
+                        a, b = t[0], t[1]
                         assert ub.get(a) is not None and ub.get(b) is not None, ("undefined / non-normalised DOT operand", prog, pid)
-                        acc += ub[a] * ub[b]
-                    v = acc // cfg.R + cfg.p
+                        if len(t) > 2 and t[2] < 0:
+                            neg += ub[a] * ub[b]
+                        else:
+                            acc += ub[a] * ub[b]
+                    K = getattr(ph, "K", 0)
+                    assert neg <= K * cfg.p * cfg.R, ("offset K too small for the negative part", prog, pid, K)
+                    v = acc // cfg.R + cfg.p + K * cfg.p
                 else:
                     v = 0
                     for slot, coef, K in terms:
@@ -792,6 +819,279 @@ def build_miller(gen: Gen):
     return raw, FA
 
 
+def build_miller_p(gen: Gen):
+    """Program MILLER of the pipelined slot file "P": one pairing per 32-lane group (one warp), signed DOT terms.
+
+    Two independent dependency chains run through the loop: the point chain (T <- 2T [+ Q], line coefficients)
+    and the f chain (f <- f^2 * line).  Their stages are co-issued in the same phases, and the first DOT of
+    the next doubling rides with the sparse product of the current one, so a doubling iteration is 4 phases
+    (2 DOT of <= 6 terms + 2 LIN) instead of 12:
+        B: LIN  sqr operands (S, B, xi-copies)        | BmF, BpF, line c
+        C: DOT  t = c0 c1, s = S B                    | X3, S, EE, Z3, BB, BE, ly', lx'
+        D: LIN  f^2 = (s - t - v t) + 2 t w           | new X, Y, Z, BB8, BE8, lines y, x
+        A: DOT  f = f^2 * line                        | XY, B, X2, YZ, E of the next doubling
+    Signed terms remove every negated copy (-y, -xi y) of the 16-lane program.  Same inputs/outputs as build_miller."""
+    cfg, p = gen.cfg, gen.cfg.p
+    assert gen.signed and gen.lanes == 32
+    D = cfg.twist == "D"
+    A_ = cfg.xi_a
+    gen.begin("MILLER")
+    raw = {n: gen.g("RAW." + n) for n in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")}
+    for sl in raw.values():
+        gen.set_ub(sl, p - 1)
+    xP, yP = gen.g("xP"), gen.g("yP")
+    xQ, yQ, nyQ = gen.fp2("xQ"), gen.fp2("yQ"), gen.fp2("nyQ")
+    gen.dot([(xP, [(raw["xP"], gen.R2)]), (yP, [(raw["yP"], gen.R2)]), (xQ[0], [(raw["xQ.x"], gen.R2)]),
+             (xQ[1], [(raw["xQ.y"], gen.R2)]), (yQ[0], [(raw["yQ.x"], gen.R2)]), (yQ[1], [(raw["yQ.y"], gen.R2)])])
+    X, Y, Z = gen.fp2("X"), gen.fp2("Y"), gen.fp2("Z")
+    BB8, BE8 = gen.fp2("BB8"), gen.fp2("BE8")
+    FA, FB = gen.f12("FA"), gen.f12("FB")
+    xi = (A_, 1)
+    b2 = f2mul((cfg.b, 0), f2inv(xi, p), p) if D else f2mul((cfg.b, 0), xi, p)
+    b3c = gen.const2("B3", (3 * b2[0] % p, 3 * b2[1] % p))
+    lin = [gen.lin(X[0], (xQ[0], 1)), gen.lin(X[1], (xQ[1], 1)), gen.lin(Y[0], (yQ[0], 1)), gen.lin(Y[1], (yQ[1], 1)),
+           gen.lin(Z[0], (gen.ONE, 1)), gen.lin(Z[1], (gen.ZERO, 1)),
+           gen.lin(nyQ[0], (yQ[0], -1)), gen.lin(nyQ[1], (yQ[1], -1)),
+           # E = 3b' Z^2 is carried as the product BB8 * BE8: initially 1 * 3b'
+           gen.lin(BB8[0], (gen.ONE, 1)), gen.lin(BB8[1], (gen.ZERO, 1)), gen.lin(BE8[0], (b3c[0], 1)), gen.lin(BE8[1], (b3c[1], 1))]
+    lin += [gen.lin(FA[k][c], (gen.ONE if (k == 0 and c == 0) else gen.ZERO, 1)) for k in range(6) for c in range(2)]
+    gen.lin_rounds(lin)
+
+    def lslots(name):
+        return {k: gen.g("%s.%s" % (name, k)) for k in ("x", "y", "tx", "ty")}
+    lines = {"y": lslots("LY"), "x": lslots("LX"), "c": lslots("LC")}
+    pos = {"y": 0, "x": 1, "c": 3} if D else {"c": 0, "x": 2, "y": 3}
+    linemap = {pos[k]: lines[k] for k in ("y", "x", "c")}
+
+    def m2(dst, u, v):       # Fp2 product
+        return [(dst[0], [(u[0], v[0]), (u[1], v[1], -1)]), (dst[1], [(u[0], v[1]), (u[1], v[0])])]
+
+    def m2fp(dst, u, s_):
+        return [(dst[0], [(u[0], s_)]), (dst[1], [(u[1], s_)])]
+
+    def line_tasks(l, ps, x_terms, y_terms):
+        neg = lambda ts: [(s_, -c) for s_, c in ts]
+        mul = lambda ts, k: [(s_, c * k) for s_, c in ts]
+        out = [gen.lin(l["x"], *x_terms), gen.lin(l["y"], *y_terms)]
+        if ps > 0:   # positions that wrap around w^6 = xi need xi * coefficient
+            out += [gen.lin(l["tx"], *(mul(x_terms, A_) + neg(y_terms))), gen.lin(l["ty"], *(x_terms + mul(y_terms, A_)))]
+        return out
+
+    def sparse_tasks(d, a):
+        tasks = []
+        for k in range(6):
+            re, im = [], []
+            for ps, l in sorted(linemap.items()):
+                i = (k - ps) % 6
+                if k - ps >= 0:
+                    re += [(a[i][0], l["x"]), (a[i][1], l["y"], -1)]
+                    im += [(a[i][0], l["y"]), (a[i][1], l["x"])]
+                else:
+                    re += [(a[i][0], l["tx"]), (a[i][1], l["ty"], -1)]
+                    im += [(a[i][0], l["ty"]), (a[i][1], l["tx"])]
+            tasks += [(d[k][0], re), (d[k][1], im)]
+        return tasks
+
+    # ---- f^2 by complex squaring over Fp6 = Fp2[v]/(v^3 - xi), v = w^2 (see Gen._f12_sqr), in three stages
+    S = [gen.fp2("SQ.S%d" % j) for j in range(3)]
+    Bq = [gen.fp2("SQ.B%d" % j) for j in range(3)]
+    d1 = {j: {"tx": gen.g("SQ.d1_%d.tx" % j), "ty": gen.g("SQ.d1_%d.ty" % j)} for j in (1, 2)}
+    dB = {j: {"tx": gen.g("SQ.dB_%d.tx" % j), "ty": gen.g("SQ.dB_%d.ty" % j)} for j in (1, 2)}
+    Tt = [gen.fp2("SQ.T%d" % j) for j in range(3)]
+    Ss = [gen.fp2("SQ.P%d" % j) for j in range(3)]
+
+    def sqr_lin_a(a):
+        c0, c1 = [a[0], a[2], a[4]], [a[1], a[3], a[5]]
+        t = []
+        for j in range(3):
+            for c in range(2):
+                t.append(gen.lin(S[j][c], (c0[j][c], 1), (c1[j][c], 1)))
+        t += [gen.lin(Bq[0][0], (c0[0][0], 1), (c1[2][0], A_), (c1[2][1], -1)),
+              gen.lin(Bq[0][1], (c0[0][1], 1), (c1[2][0], 1), (c1[2][1], A_))]
+        for j in (1, 2):
+            for c in range(2):
+                t.append(gen.lin(Bq[j][c], (c0[j][c], 1), (c1[j - 1][c], 1)))
+        for j in (1, 2):   # xi-copies of the second operands (only v_1, v_2 ever wrap)
+            t += [gen.lin(d1[j]["tx"], (c1[j][0], A_), (c1[j][1], -1)), gen.lin(d1[j]["ty"], (c1[j][0], 1), (c1[j][1], A_)),
+                  gen.lin(dB[j]["tx"], (c0[j][0], A_), (c1[j - 1][0], A_), (c0[j][1], -1), (c1[j - 1][1], -1)),
+                  gen.lin(dB[j]["ty"], (c0[j][0], 1), (c1[j - 1][0], 1), (c0[j][1], A_), (c1[j - 1][1], A_))]
+        return t
+
+    def fp6_dots(dst, u, v, dv):
+        out = []
+        for k in range(3):
+            re, im = [], []
+            for i in range(3):
+                j = (k - i) % 3
+                if i <= k:
+                    re += [(u[i][0], v[j][0]), (u[i][1], v[j][1], -1)]
+                    im += [(u[i][0], v[j][1]), (u[i][1], v[j][0])]
+                else:       # v^3 = xi
+                    re += [(u[i][0], dv[j]["tx"]), (u[i][1], dv[j]["ty"], -1)]
+                    im += [(u[i][0], dv[j]["ty"]), (u[i][1], dv[j]["tx"])]
+            out += [(dst[k][0], re), (dst[k][1], im)]
+        return out
+
+    def sqr_dot(a):
+        c0, c1 = [a[0], a[2], a[4]], [a[1], a[3], a[5]]
+        return fp6_dots(Tt, c0, c1, d1) + fp6_dots(Ss, S, Bq, dB)
+
+    def sqr_lin_b(d):
+        nc0, nc1 = [d[0], d[2], d[4]], [d[1], d[3], d[5]]
+        t = [gen.lin(nc0[0][0], (Ss[0][0], 1), (Tt[0][0], -1), (Tt[2][0], -A_), (Tt[2][1], 1)),
+             gen.lin(nc0[0][1], (Ss[0][1], 1), (Tt[0][1], -1), (Tt[2][0], -1), (Tt[2][1], -A_))]
+        for j in (1, 2):
+            for c in range(2):
+                t.append(gen.lin(nc0[j][c], (Ss[j][c], 1), (Tt[j][c], -1), (Tt[j - 1][c], -1)))
+        for j in range(3):
+            for c in range(2):
+                t.append(gen.lin(nc1[j][c], (Tt[j][c], 2)))
+        return t
+
+    # ---- doubling: homogeneous projective, E = 3b'Z^2 = BB8 * BE8
+    XY, Bd, X2, YZ, E = gen.fp2("XY"), gen.fp2("B"), gen.fp2("X2"), gen.fp2("YZ"), gen.fp2("E")
+    BmF, BpF = gen.fp2("BmF"), gen.fp2("BpF")
+    X3, Sd, EE, Z3, BB, BE = gen.fp2("X3"), gen.fp2("S"), gen.fp2("EE"), gen.fp2("Z3"), gen.fp2("BB"), gen.fp2("BE")
+    LYp, LXp = gen.fp2("LYp"), gen.fp2("LXp")
+
+    def dbl_dot1():
+        return m2(XY, X, Y) + m2(Bd, Y, Y) + m2(X2, X, X) + m2(YZ, Y, Z) + m2(E, BB8, BE8)
+
+    def dbl_lin1():
+        t = [gen.lin(BmF[0], (Bd[0], 1), (E[0], -3)), gen.lin(BmF[1], (Bd[1], 1), (E[1], -3)),
+             gen.lin(BpF[0], (Bd[0], 1), (E[0], 3)), gen.lin(BpF[1], (Bd[1], 1), (E[1], 3))]
+        return t + line_tasks(lines["c"], pos["c"], [(Bd[0], 1), (E[0], -1)], [(Bd[1], 1), (E[1], -1)])
+
+    def dbl_dot2():
+        return (m2(X3, XY, BmF) + m2(Sd, BpF, BpF) + m2(EE, E, E) + m2(Z3, Bd, YZ) + m2(BB, Bd, Bd) + m2(BE, Bd, E) +
+                m2fp(LYp, YZ, yP) + m2fp(LXp, X2, xP))
+
+    def dbl_lin2():
+        # (4X3, 4Y3, 4Z3) = (2 XY (B-F), (B+F)^2 - 12 E^2, 8 B YZ);  ly = 2 YZ yP,  lx = -3 X^2 xP
+        t = [gen.lin(X[0], (X3[0], 2)), gen.lin(X[1], (X3[1], 2)),
+             gen.lin(Y[0], (Sd[0], 1), (EE[0], -12)), gen.lin(Y[1], (Sd[1], 1), (EE[1], -12)),
+             gen.lin(Z[0], (Z3[0], 8)), gen.lin(Z[1], (Z3[1], 8)),
+             gen.lin(BB8[0], (BB[0], 8)), gen.lin(BB8[1], (BB[1], 8)), gen.lin(BE8[0], (BE[0], 8)), gen.lin(BE8[1], (BE[1], 8))]
+        t += line_tasks(lines["y"], pos["y"], [(LYp[0], 2)], [(LYp[1], 2)])
+        t += line_tasks(lines["x"], pos["x"], [(LXp[0], -3)], [(LXp[1], -3)])
+        return t
+
+    # ---- mixed addition T += Q' = (Qx, Qy) with its line, four DOT + four LIN stages
+    yqZ, xqZ, TH, LA = gen.fp2("yqZ"), gen.fp2("xqZ"), gen.fp2("TH"), gen.fp2("LA")
+    Cc, Dd, LCp = gen.fp2("Cc"), gen.fp2("Dd"), gen.fp2("LCp")
+    Ee, Ff, Gg, H, GmH = gen.fp2("Ee"), gen.fp2("Ff"), gen.fp2("Gg"), gen.fp2("H"), gen.fp2("GmH")
+    AX3, ATt, EY, AZ3, EE2 = gen.fp2("AX3"), gen.fp2("ATt"), gen.fp2("EY"), gen.fp2("AZ3"), gen.fp2("EE2")
+
+    def add_dot1(Qx, Qy):
+        return m2(yqZ, Qy, Z) + m2(xqZ, Qx, Z) + m2(E, BB8, BE8)
+
+    def add_lin1():
+        return [gen.lin(TH[0], (Y[0], 1), (yqZ[0], -1)), gen.lin(TH[1], (Y[1], 1), (yqZ[1], -1)),
+                gen.lin(LA[0], (X[0], 1), (xqZ[0], -1)), gen.lin(LA[1], (X[1], 1), (xqZ[1], -1))]
+
+    def add_dot2(Qx, Qy):
+        # lc = theta xQ - lam yQ
+        t = m2(Cc, TH, TH) + m2(Dd, LA, LA)
+        t += [(LCp[0], [(TH[0], Qx[0]), (TH[1], Qx[1], -1), (LA[0], Qy[0], -1), (LA[1], Qy[1])]),
+              (LCp[1], [(TH[0], Qx[1]), (TH[1], Qx[0]), (LA[0], Qy[1], -1), (LA[1], Qy[0], -1)])]
+        return t + m2fp(LYp, LA, yP) + m2fp(LXp, TH, xP)
+
+    def add_lin2():
+        return (line_tasks(lines["y"], pos["y"], [(LYp[0], 1)], [(LYp[1], 1)]) +
+                line_tasks(lines["x"], pos["x"], [(LXp[0], -1)], [(LXp[1], -1)]) +
+                line_tasks(lines["c"], pos["c"], [(LCp[0], 1)], [(LCp[1], 1)]))
+
+    def add_dot3():
+        return m2(Ee, LA, Dd) + m2(Ff, Z, Cc) + m2(Gg, X, Dd)
+
+    def add_lin3():
+        return [gen.lin(H[0], (Ee[0], 1), (Ff[0], 1), (Gg[0], -2)), gen.lin(H[1], (Ee[1], 1), (Ff[1], 1), (Gg[1], -2)),
+                gen.lin(GmH[0], (Gg[0], 3), (Ee[0], -1), (Ff[0], -1)), gen.lin(GmH[1], (Gg[1], 3), (Ee[1], -1), (Ff[1], -1))]
+
+    def add_dot4():
+        return m2(AX3, LA, H) + m2(ATt, TH, GmH) + m2(EY, Ee, Y) + m2(AZ3, Z, Ee) + m2(EE2, Ee, Ee)
+
+    def add_lin4():
+        # E' = E * (lam^3)^2: carried as BB8 = E, BE8 = Ee^2
+        return [gen.lin(BB8[0], (E[0], 1)), gen.lin(BB8[1], (E[1], 1)), gen.lin(BE8[0], (EE2[0], 1)), gen.lin(BE8[1], (EE2[1], 1)),
+                gen.lin(X[0], (AX3[0], 1)), gen.lin(X[1], (AX3[1], 1)),
+                gen.lin(Y[0], (ATt[0], 1), (EY[0], -1)), gen.lin(Y[1], (ATt[1], 1), (EY[1], -1)),
+                gen.lin(Z[0], (AZ3[0], 1)), gen.lin(Z[1], (AZ3[1], 1))]
+
+    def lin1(tasks):
+        assert len(tasks) <= gen.lanes, len(tasks)
+        gen.lin_rounds(tasks)
+
+    def add_step(Qx, Qy, more):
+        """FB = f^2, dbl line ready.  Ends with f in FA and (if `more`) the first DOT of the next doubling issued."""
+        gen.dot(sparse_tasks(FA, FB) + add_dot1(Qx, Qy))
+        lin1(add_lin1())
+        gen.dot(add_dot2(Qx, Qy))
+        lin1(add_lin2())
+        gen.dot(sparse_tasks(FB, FA) + add_dot3())
+        lin1(add_lin3() + [gen.lin(FA[k][c], (FB[k][c], 1)) for k in range(6) for c in range(2)])
+        gen.dot(add_dot4())
+        lin1(add_lin4())
+        if more:
+            gen.dot(dbl_dot1())
+
+    INV_F, INV_T = 64 * p, 4096 * p
+    fslots = [FA[k][c] for k in range(6) for c in range(2)]
+    tslots = [X[0], X[1], Y[0], Y[1], Z[0], Z[1], BB8[0], BB8[1], BE8[0], BE8[1]]
+    digits = naf(cfg.loop) if cfg.loop_naf else [int(c) for c in bin(cfg.loop)[2:]]
+    assert digits[0] == 1
+    body = digits[1:]
+    gen.dot(dbl_dot1())
+    for n_, dgt in enumerate(body):
+        last = n_ == len(body) - 1
+        more = (not last) or False
+        lin1(sqr_lin_a(FA) + dbl_lin1())
+        gen.dot(sqr_dot(FA) + dbl_dot2())
+        lin1(sqr_lin_b(FB) + dbl_lin2())
+        if dgt == 0:
+            gen.dot(sparse_tasks(FA, FB) + (dbl_dot1() if more else []))
+        elif dgt == 1:
+            add_step(xQ, yQ, more)
+        else:
+            add_step(xQ, nyQ, more)
+        gen.check_le(fslots, INV_F)
+        gen.check_le(tslots, INV_T)
+    if D:
+        # Q1 = pi(Q), -Q2 = -pi^2(Q):  pi(x, y) = (conj(x) g2, conj(y) g3), g_k = xi^(k(p-1)/6)
+        g1 = f2pow(xi, (p - 1) // 6, p)
+        g2c = gen.const2("G2", f2pow(g1, 2, p))
+        g3c = gen.const2("G3", f2pow(g1, 3, p))
+        Q1x, Q1y, Q2x, Q2y, nQ2y = gen.fp2("Q1x"), gen.fp2("Q1y"), gen.fp2("Q2x"), gen.fp2("Q2y"), gen.fp2("nQ2y")
+
+        def frobq(dx, dy, sx, sy):
+            # conj(s) * g = (s.x g.x + s.y g.y) + (s.x g.y - s.y g.x) i
+            return [(dx[0], [(sx[0], g2c[0]), (sx[1], g2c[1])]), (dx[1], [(sx[0], g2c[1]), (sx[1], g2c[0], -1)]),
+                    (dy[0], [(sy[0], g3c[0]), (sy[1], g3c[1])]), (dy[1], [(sy[0], g3c[1]), (sy[1], g3c[0], -1)])]
+        gen.dot(frobq(Q1x, Q1y, xQ, yQ))
+        gen.dot(frobq(Q2x, Q2y, Q1x, Q1y))
+        lin1([gen.lin(nQ2y[0], (Q2y[0], -1)), gen.lin(nQ2y[1], (Q2y[1], -1))])
+
+        def tail_add(Qx, Qy, src, dst):
+            gen.dot(add_dot1(Qx, Qy))
+            lin1(add_lin1())
+            gen.dot(add_dot2(Qx, Qy))
+            lin1(add_lin2())
+            gen.dot(sparse_tasks(dst, src) + add_dot3())
+            lin1(add_lin3())
+            gen.dot(add_dot4())
+            lin1(add_lin4())
+        tail_add(Q1x, Q1y, FA, FB)
+        # the last addition only contributes its line: the point update is not needed
+        gen.dot(add_dot1(Q2x, nQ2y))
+        lin1(add_lin1())
+        gen.dot(add_dot2(Q2x, nQ2y))
+        lin1(add_lin2())
+        gen.dot(sparse_tasks(FA, FB))
+    else:
+        gen.f12_conj(FA, FA)  # x < 0
+    return raw, FA
+
+
 def build_mulacc(gen: Gen):
     """Programs MUL_AB (FB = FA * GB) and MUL_BA (FA = FB * GB) for product trees."""
     p = gen.cfg.p
@@ -998,9 +1298,9 @@ class Sim:
                     outs.append((dst, v))
                     continue
                 if ph.kind == "DOT":
-                    t = sum(self.rd(a) * self.rd(b) for a, b in terms)
+                    t = sum((-1 if (len(tm_) > 2 and tm_[2] < 0) else 1) * self.rd(tm_[0]) * self.rd(tm_[1]) for tm_ in terms)
                     m = (-t * pinv) % cfg.R
-                    v = (t + m * cfg.p) // cfg.R
+                    v = (t + m * cfg.p) // cfg.R + getattr(ph, "K", 0) * cfg.p
                 else:
                     v = 0
                     for s, coef, K in terms:
@@ -1019,9 +1319,12 @@ class Sim:
 
 
 def build_all(cfg):
-    """Two independent slot files: "M" (MILLER, MUL_AB, MUL_BA) and "F" (FINALEXP)."""
+    """Three independent slot files: "M" (16-lane MILLER, MUL_AB, MUL_BA), "F" (FINALEXP) and "P" (32-lane
+    pipelined MILLER with signed terms: the latency path)."""
     gm, gf = Gen(cfg), Gen(cfg, lanes=32, tm=6, split=True)
+    gp = Gen(cfg, lanes=32, tm=6, signed=True)
     io = {}
+    io["p_miller_in"], io["P_FA"] = build_miller_p(gp)
     io["miller_in"], io["FA"] = build_miller(gm)
     _, io["FB"], io["GB"] = build_mulacc(gm)
     io["F_FA"], io["OUT"] = build_final_exp(gf)
@@ -1040,7 +1343,7 @@ def build_all(cfg):
             for c in range(2):
                 gm.set_ub(io["RAWF"][k][c], p - 1)
         gm.dot([(dst[k][c], [(io["RAWF"][k][c], gm.R2)]) for k in range(6) for c in range(2)])
-    return {"M": gm, "F": gf}, io
+    return {"M": gm, "F": gf, "P": gp}, io
 
 
 # ======================================================================================
@@ -1055,6 +1358,8 @@ def verify_all(cfg, gens, io):
     rep = {}
     rep["MILLER"], ubm = gm.verify_program("MILLER", {s: p - 1 for s in raw.values()})
     f_ub = max(ubm[FA[k][c]] for k in range(6) for c in range(2))
+    rep["P.MILLER"], ubp = gens["P"].verify_program("MILLER", {s: p - 1 for s in io["p_miller_in"].values()})
+    assert max(ubp[io["P_FA"][k][c]] for k in range(6) for c in range(2)) <= 64 * p, "P Miller output exceeds the product-tree input bound"
     # product trees: operands are Miller outputs or earlier products
     init = {reg[k][c]: 64 * p for reg in (FA, FB, GB) for k in range(6) for c in range(2)}
     assert f_ub <= 64 * p
@@ -1079,13 +1384,15 @@ def emit_tables(path):
         bits = verify_all(cfg, gens, io)
         print(cfg.name, "worst-case value bits per program:", bits, "of", cfg.W * cfg.L)
         for tag, gen in gens.items():
-            n = "%s_%s" % (cfg.name, tag)
+            n = "%s_%s" % (cfg.name, {"P": "MP"}.get(tag, tag))
             nsg = gen._nslots
             ref = lambda s, nsg=nsg: s[1] if s[0] == "g" else nsg + s[1]
             out.append("// ---- %s: W=%d L=%d, %d group slots, %d constant slots, %d phases" % (n, cfg.W, cfg.L, nsg, len(gen.cvals), len(gen.phases)))
             out.append("struct %s {" % n)
             out.append("  static constexpr int W = %d, L = %d, NSG = %d, NCONST = %d, NPHASE = %d;" % (cfg.W, cfg.L, nsg, len(gen.cvals), len(gen.phases)))
             out.append("  static constexpr int LANES = %d, TM = %d, REC = %d;  // lanes per group, max DOT terms, u16 per lane record" % (gen.lanes, gen.tm, 2 * gen.tm + 2))
+            out.append("  static constexpr bool SIGNED = %s;  // DOT terms may be negative (bit 15 of the first operand), offset K p in the header" % ("true" if gen.signed else "false"))
+            out.append("  static constexpr int NS = NSG + NCONST;  // slots of one group file: group slots, then a private copy of the constants")
             out.append("  static constexpr uint32_t N0 = 0x%xu;" % cfg.n0)
             out.append("  static constexpr int FP_BYTES = %d;" % (32 if cfg.name == "BN254" else 48))
             out.append("  HD static constexpr uint32_t p(int i) {")
@@ -1094,11 +1401,11 @@ def emit_tables(path):
             out.append("  }")
             for pname, prog in gen.programs.items():
                 out.append("  static constexpr int %s_LEN = %d;" % (pname, len(prog)))
-            if tag == "M":
-                raw = io["miller_in"]
+            if tag in ("M", "P"):
+                raw = io["miller_in"] if tag == "M" else io["p_miller_in"]
                 out.append("  static constexpr int IN_XP = %d, IN_YP = %d, IN_XQX = %d, IN_XQY = %d, IN_YQX = %d, IN_YQY = %d;" % tuple(
                     ref(raw[k]) for k in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")))
-                regs_ = (("FA", io["FA"]), ("FB", io["FB"]), ("GB", io["GB"]), ("RAWF", io["RAWF"]))
+                regs_ = (("FA", io["FA"]), ("FB", io["FB"]), ("GB", io["GB"]), ("RAWF", io["RAWF"])) if tag == "M" else (("FA", io["P_FA"]),)
             else:
                 regs_ = (("FA", io["F_FA"]), ("OUT", io["OUT"]))
             for nm, reg in regs_:
@@ -1117,7 +1424,7 @@ def emit_tables(path):
             TM, REC = gen.tm, 2 * gen.tm + 2
             hdr, rec = [], []
             for ph in gen.phases:
-                hdr.append({"DOT": 0, "LIN": 1, "INV": 2}[ph.kind] | (ph.T << 8) | (len(ph.tasks) << 16))
+                hdr.append({"DOT": 0, "LIN": 1, "INV": 2}[ph.kind] | (ph.T << 8) | ((len(ph.tasks) & 0xFF) << 16) | (getattr(ph, "K", 0) << 24))
                 for lane in range(gen.lanes):
                     r = [0xFFFF] + [ref(gen.ZERO)] * (2 * TM) + [0]
                     if ph.kind == "LIN":
@@ -1131,6 +1438,9 @@ def emit_tables(path):
                                 r[1] = ref(term[0])
                             elif ph.kind == "DOT":
                                 r[1 + t], r[1 + TM + t] = ref(term[0]), ref(term[1])
+                                assert r[1 + t] < 0x8000
+                                if len(term) > 2 and term[2] < 0:
+                                    r[1 + t] |= 0x8000   # minus sign: the interpreter negates the first operand
                             else:
                                 slot, coef, K = term
                                 r[1 + t] = ref(slot)
