@@ -206,7 +206,7 @@ using namespace bgls;
 // device copies of the machine tables of one curve
 struct MachDev {
     MachTables m{}, f{}, p{};   // 16-lane product file, final-exponentiation file, pipelined 32-lane Miller file
-    const uint16_t *miller = nullptr, *mul_ab = nullptr, *mul_ba = nullptr, *import_a = nullptr, *miller_p = nullptr;
+    const uint16_t *miller = nullptr, *mul_ab = nullptr, *mul_ba = nullptr, *import_a = nullptr, *miller_p = nullptr, *mulacc_p = nullptr;
     const uint16_t *finalexp = nullptr, *export_ = nullptr;
     void* blob = nullptr;
 };
@@ -384,6 +384,7 @@ template <class M, class MT, class F, class FT, class P, class PT> int upload_ma
         {PT::hdr(), sizeof(uint32_t) * P::NPHASE, (const void**)&d.p.hdr},
         {PT::rec(), sizeof(uint16_t) * P::NPHASE * P::LANES * P::REC, (const void**)&d.p.rec},
         {PT::prog_MILLER(), sizeof(uint16_t) * P::MILLER_LEN, (const void**)&d.miller_p},
+        {PT::prog_MULACC(), sizeof(uint16_t) * P::MULACC_LEN, (const void**)&d.mulacc_p},
     };
     size_t total = 0;
     for (const Part& p : parts) total += align_up(p.bytes);
@@ -400,6 +401,7 @@ template <class M, class MT, class F, class FT, class P, class PT> int upload_ma
     CU(cudaFuncSetAttribute(k_mach_import<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(1)));
     CU(cudaFuncSetAttribute(k_mach_miller32<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<P>(MP_MAXW)));
+    CU(cudaFuncSetAttribute(k_mach_tree32<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<P>(MP_MAXW)));
     return BGLS_OK;
 }
 
@@ -412,23 +414,29 @@ template <class M> struct PFile;
 template <> struct PFile<mtab::BN254_M> { using type = mtab::BN254_MP; };
 template <> struct PFile<mtab::BLS381_M> { using type = mtab::BLS381_MP; };
 
+// Miller loops of n pairs.  fuse: the values are multiplied per block inside the kernel (product pipelines);
+// returns the number of values written to `vals` (n without fusion).
 template <class M>
-void launch_miller(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, uint32_t* vals, cudaStream_t s) {
-    if (n == 0) return;
+size_t launch_miller(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, uint32_t* vals, cudaStream_t s,
+                     bool fuse = false) {
+    if (n == 0) return 0;
     if (!ctx->miller16) {
         // one pairing per warp; the block size spreads the pairs over all SMs (small products) up to 16 warps per SM
         using P = typename PFile<M>::type;
         size_t wpb = (n + ctx->sms - 1) / ctx->sms;
         if (wpb > (size_t)MP_MAXW) wpb = MP_MAXW;
-        k_mach_miller32<P><<<(unsigned)((n + wpb - 1) / wpb), (unsigned)wpb * 32, mach_smem_bytes<P>((int)wpb), s>>>(d.p, d.miller_p, P::MILLER_LEN, d_g1, d_g2, n, vals);
+        const size_t nb = (n + wpb - 1) / wpb;
+        k_mach_miller32<P><<<(unsigned)nb, (unsigned)wpb * 32, mach_smem_bytes<P>((int)wpb), s>>>(d.p, d.miller_p, P::MILLER_LEN, d.mulacc_p, fuse ? 1 : 0,
+                                                                                             d_g1, d_g2, n, vals);
         ctx->launches++;
-        return;
+        return fuse ? nb : n;
     }
     if (n <= MSMALL)
         k_mach_miller<M, 1><<<(unsigned)((n + MWPB - 1) / MWPB), MWPB * 32, mach_smem_bytes<M>(MWPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, vals);
     else
         k_mach_miller<M, 2><<<(unsigned)((n + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.miller, M::MILLER_LEN, d_g1, d_g2, n, vals);
     ctx->launches++;
+    return n;
 }
 template <class M> size_t mach_val_bytes() { return (size_t)12 * M::L * sizeof(uint32_t); }
 template <class M> size_t mach_work_bytes(size_t n) { return align_up((n + 2) * mach_val_bytes<M>()) + align_up((n / MCHUNK + 3) * mach_val_bytes<M>()); }
@@ -442,6 +450,15 @@ int mach_tree(bgls_ctx* ctx, const MachDev& d, uint32_t* buf0, uint32_t* buf1, s
         ctx->launches++;
         std::swap(cur, oth);
         cnt = 1;
+    }
+    while (cnt > 1 && !ctx->miller16) {   // binary in-block trees, 16 values per block and level
+        using P = typename PFile<M>::type;
+        const size_t wpb = cnt < (size_t)MP_MAXW ? cnt : (size_t)MP_MAXW;
+        const size_t nout = (cnt + wpb - 1) / wpb;
+        k_mach_tree32<P><<<(unsigned)nout, (unsigned)wpb * 32, mach_smem_bytes<P>((int)wpb), s>>>(d.p, d.mulacc_p, cur, cnt, oth);
+        ctx->launches++;
+        std::swap(cur, oth);
+        cnt = nout;
     }
     while (cnt > 1) {
         const size_t nout = (cnt + MCHUNK - 1) / MCHUNK;
@@ -461,10 +478,10 @@ int mach_pairing(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uin
     uint32_t* buf0 = (uint32_t*)work;
     uint32_t* buf1 = (uint32_t*)((char*)work + align_up((n + 2) * mach_val_bytes<M>()));
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
-    launch_miller<M>(ctx, d, d_g1, d_g2, n, buf0, s);
+    const size_t cnt = launch_miller<M>(ctx, d, d_g1, d_g2, n, buf0, s, true);
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
     uint32_t* res;
-    int rc = mach_tree<M>(ctx, d, buf0, buf1, n, &res, s);
+    int rc = mach_tree<M>(ctx, d, buf0, buf1, cnt, &res, s);
     if (rc) return rc;
     k_mach_finish<F, M><<<1, MFIN_THREADS, mach_smem_bytes<F>(1), s>>>(d.f, do_final ? d.finalexp : d.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN,
                                                            res, 1, d_out, d_flag, nullptr);

@@ -116,42 +116,106 @@ __global__ void __launch_bounds__(MWPB * 32) k_mach_miller(MachTables tb, const 
 // Latency path: one pairing per warp running the pipelined program of the signed 32-lane slot file P
 // (tools/gen_machine.py: build_miller_p).  blockDim.x / 32 pairings per block, chosen by the host so that the
 // grid covers all SMs with as many resident warps per SM sub-partition as the product offers.
+// In-block binary product tree over the FA registers of the first `wact` group files of the block (one warp each,
+// P::MULACC multiplies in place): log2 levels, each one Fp12 product deep.  Every warp of the block must call it.
+// Afterwards FA of group 0 holds the product.
+template <class P>
+__device__ __forceinline__ void mach_block_tree(uint32_t* gbase, const MachTables& tb, const uint16_t* __restrict__ prog_mul,
+                                                int wact, int warp, int lane) {
+    constexpr int L = P::L;
+    MachView<P> mv;
+    mv.gs = gbase + (size_t)warp * P::NS * L;
+    for (int stride = 1; stride < wact; stride <<= 1) {
+        __syncthreads();   // the partner's product of the previous level is complete
+        if ((warp & (2 * stride - 1)) == 0 && warp + stride < wact) {
+            const uint32_t* pg = gbase + (size_t)(warp + stride) * P::NS * L;
+            for (int idx = lane; idx < 12 * L; idx += 32) {
+                const int k = idx / L, i = idx % L;
+                mv.gs[i * P::NS + P::GB0 + k] = pg[i * P::NS + P::FA0 + k];
+            }
+            __syncwarp();
+            mach_run<P>(mv, tb, prog_mul, P::MULACC_LEN, lane);
+        }
+    }
+}
+
 template <class P>
 __global__ void __launch_bounds__(512) k_mach_miller32(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+                                                      const uint16_t* __restrict__ prog_mul, int fuse,
                                                       const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                       size_t n, uint32_t* __restrict__ vals) {
+    // fuse != 0: vals[block] = product of the block's Miller values; fuse == 0: vals[pair] = Miller value of the pair
     extern __shared__ uint32_t sm[];
     constexpr int L = P::L, FB = P::FP_BYTES;
     static_assert(P::LANES == 32, "one warp per pairing");
     const int wpb = blockDim.x >> 5;
     uint32_t* gbase = mach_stage_tables<P>(sm, tb, wpb);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t pair = (size_t)blockIdx.x * wpb + warp;
-    if (pair >= n) return;
+    const size_t first = (size_t)blockIdx.x * wpb;
+    const size_t pair = first + warp;
+    const int wact = (int)(n - first < (size_t)wpb ? n - first : (size_t)wpb);   // pairings of this block
     MachView<P> mv;
     mv.gs = gbase + (size_t)warp * P::NS * L;
-    bool zero = true, flag = false;
-    if (lane < 6) {   // lanes 0..5 convert one coordinate each
-        const uint8_t* src = lane < 2 ? g1 + pair * 2 * FB + lane * FB : g2 + pair * 4 * FB + (lane - 2) * FB;
-        const int slot = lane == 0 ? P::IN_XP : lane == 1 ? P::IN_YP : lane == 2 ? P::IN_XQY : lane == 3 ? P::IN_XQX : lane == 4 ? P::IN_YQY : P::IN_YQX;
-        uint32_t v[L];
-        mach_limbs_from_be<P>(v, src);
-        uint32_t any = 0;
+    if (pair < n) {
+        bool zero = true, flag = false;
+        if (lane < 6) {   // lanes 0..5 convert one coordinate each
+            const uint8_t* src = lane < 2 ? g1 + pair * 2 * FB + lane * FB : g2 + pair * 4 * FB + (lane - 2) * FB;
+            const int slot = lane == 0 ? P::IN_XP : lane == 1 ? P::IN_YP : lane == 2 ? P::IN_XQY : lane == 3 ? P::IN_XQX : lane == 4 ? P::IN_YQY : P::IN_YQX;
+            uint32_t v[L];
+            mach_limbs_from_be<P>(v, src);
+            uint32_t any = 0;
 #pragma unroll
-        for (int i = 0; i < L; i++) any |= v[i];
-        zero = any == 0;
-        flag = FB == 48 && (lane == 0 || lane == 2) && (src[0] & 0x40);
-        mach_store<P>(mv, slot, v);
+            for (int i = 0; i < L; i++) any |= v[i];
+            zero = any == 0;
+            flag = FB == 48 && (lane == 0 || lane == 2) && (src[0] & 0x40);
+            mach_store<P>(mv, slot, v);
+        }
+        const unsigned zb = __ballot_sync(0xFFFFFFFFu, zero) & 0x3Fu;
+        const unsigned fb = __ballot_sync(0xFFFFFFFFu, flag) & 0x3Fu;
+        const bool inf = ((zb & 0x3u) == 0x3u) || ((zb & 0x3Cu) == 0x3Cu) || (fb & 0x5u);
+        __syncwarp();
+        mach_run<P>(mv, tb, prog, plen, lane);
+        if (inf && lane < 12) {   // e(P, Q) = 1 when either point is the point at infinity
+            uint32_t v[L];
+            mach_load<P>(v, mv, lane == 0 ? P::ONE : P::ZERO);
+            mach_store<P>(mv, P::FA0 + lane, v);
+        }
+        __syncwarp();
     }
-    const unsigned zb = __ballot_sync(0xFFFFFFFFu, zero) & 0x3Fu;
-    const unsigned fb = __ballot_sync(0xFFFFFFFFu, flag) & 0x3Fu;
-    const bool inf = ((zb & 0x3u) == 0x3u) || ((zb & 0x3Cu) == 0x3Cu) || (fb & 0x5u);
-    __syncwarp();
-    mach_run<P>(mv, tb, prog, plen, lane);
-    if (lane < 12) {
+    if (fuse) mach_block_tree<P>(gbase, tb, prog_mul, wact, warp, lane);   // one output per block
+    if ((fuse ? warp == 0 : pair < n) && lane < 12) {
         uint32_t v[L];
-        mach_load<P>(v, mv, inf ? (lane == 0 ? P::ONE : P::ZERO) : P::FA0 + lane);
-        uint32_t* o = vals + (pair * 12 + lane) * L;
+        mach_load<P>(v, mv, P::FA0 + lane);
+        uint32_t* o = vals + ((fuse ? (size_t)blockIdx.x : pair) * 12 + lane) * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) o[i] = v[i];
+    }
+}
+
+// ---------------------------------------------------------------- K2p
+// One level of the product tree: every block multiplies up to blockDim.x / 32 values (machine form) into one.
+template <class P>
+__global__ void __launch_bounds__(512) k_mach_tree32(MachTables tb, const uint16_t* __restrict__ prog_mul,
+                                                    const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+    extern __shared__ uint32_t sm[];
+    constexpr int L = P::L;
+    const int wpb = blockDim.x >> 5;
+    uint32_t* gbase = mach_stage_tables<P>(sm, tb, wpb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t first = (size_t)blockIdx.x * wpb;
+    const int wact = (int)(n - first < (size_t)wpb ? n - first : (size_t)wpb);
+    MachView<P> mv;
+    mv.gs = gbase + (size_t)warp * P::NS * L;
+    if (warp < wact) {
+        const uint32_t* src = in + (first + warp) * 12 * L;
+        for (int idx = lane; idx < 12 * L; idx += 32) mv.gs[(idx % L) * P::NS + P::FA0 + idx / L] = src[idx];
+        __syncwarp();
+    }
+    mach_block_tree<P>(gbase, tb, prog_mul, wact, warp, lane);
+    if (warp == 0 && lane < 12) {
+        uint32_t v[L];
+        mach_load<P>(v, mv, P::FA0 + lane);
+        uint32_t* o = out + ((size_t)blockIdx.x * 12 + lane) * L;
 #pragma unroll
         for (int i = 0; i < L; i++) o[i] = v[i];
     }

@@ -101,6 +101,7 @@ static int mach_pairing(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t*
     constexpr int L = MM::L, FB = MM::FP_BYTES;
     static_assert(PM::L == MM::L && PM::W == MM::W, "limb layouts must agree");
     HostMach<MM, MT> acc;   // accumulator group: product tree through MUL_AB / MUL_BA
+    HostMach<PM, PT> accp;  // P file: in-place MULACC (the block trees of k_mach_miller32 / k_mach_tree32)
     bool have = false, in_a = true;
     uint32_t one[L], zero[L];
     acc.get(MM::ONE, one);
@@ -125,7 +126,15 @@ static int mach_pairing(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t*
             for (int k = 0; k < 12; k++) m.get(PM::FA0 + k, f[k]);
         }
         if (dbg_f && i == 0) memcpy(dbg_f, f, sizeof(f));
-        if (!have) {
+        if constexpr (PM::SIGNED) {
+            if (!have) {
+                for (int k = 0; k < 12; k++) accp.set(PM::FA0 + k, f[k]);
+                have = true;
+            } else {
+                for (int k = 0; k < 12; k++) accp.set(PM::GB0 + k, f[k]);
+                accp.run(PT::prog_MULACC(), PM::MULACC_LEN);
+            }
+        } else if (!have) {
             for (int k = 0; k < 12; k++) acc.set(MM::FA0 + k, f[k]);
             have = true; in_a = true;
         } else {
@@ -137,6 +146,7 @@ static int mach_pairing(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t*
     uint32_t f[12][L];
     for (int k = 0; k < 12; k++) {
         if (!have) memcpy(f[k], k == 0 ? one : zero, sizeof(one));
+        else if constexpr (PM::SIGNED) accp.get(PM::FA0 + k, f[k]);
         else acc.get((in_a ? MM::FA0 : MM::FB0) + k, f[k]);
     }
     HostMach<FM, FT> fe;

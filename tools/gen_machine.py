@@ -1092,6 +1092,44 @@ def build_miller_p(gen: Gen):
     return raw, FA
 
 
+TREE_P = 48   # invariant of the P-file product tree: every operand and product is below TREE_P * p
+
+
+def build_mulacc_p(gen: Gen, FA):
+    """Program MULACC of the signed 32-lane file: FA <- FA * GB in place (product trees).  Every dot of 12 terms is
+    computed as two half dots on two lanes (temporaries), then one LIN phase sums the halves into FA."""
+    p, A_ = gen.cfg.p, gen.cfg.xi_a
+    GB = gen.f12("GB")
+    gen.begin("MULACC")
+    for k in range(6):
+        for c in range(2):
+            gen.set_ub(FA[k][c], TREE_P * p)
+            gen.set_ub(GB[k][c], TREE_P * p)
+    dv = {j: {"tx": gen.g("MUL.d%d.tx" % j), "ty": gen.g("MUL.d%d.ty" % j)} for j in range(1, 6)}   # xi * GB_j (j = 0 never wraps)
+    lin = []
+    for j in range(1, 6):
+        lin += [gen.lin(dv[j]["tx"], (GB[j][0], A_), (GB[j][1], -1)), gen.lin(dv[j]["ty"], (GB[j][0], 1), (GB[j][1], A_))]
+    gen.lin_rounds(lin)
+    halves, comb = [], []
+    for k in range(6):
+        re, im = [], []
+        for i in range(6):
+            j = (k - i) % 6
+            if i <= k:
+                re.append([(FA[i][0], GB[j][0]), (FA[i][1], GB[j][1], -1)])
+                im.append([(FA[i][0], GB[j][1]), (FA[i][1], GB[j][0])])
+            else:
+                re.append([(FA[i][0], dv[j]["tx"]), (FA[i][1], dv[j]["ty"], -1)])
+                im.append([(FA[i][0], dv[j]["ty"]), (FA[i][1], dv[j]["tx"])])
+        for c, parts in ((0, re), (1, im)):
+            lo, hi = gen.g("MUL.lo%d_%d" % (k, c)), gen.g("MUL.hi%d_%d" % (k, c))
+            halves += [(lo, sum(parts[:3], [])), (hi, sum(parts[3:], []))]
+            comb.append(gen.lin(FA[k][c], (lo, 1), (hi, 1)))
+    gen.dot(halves)
+    gen.lin_rounds(comb)
+    return GB
+
+
 def build_mulacc(gen: Gen):
     """Programs MUL_AB (FB = FA * GB) and MUL_BA (FA = FB * GB) for product trees."""
     p = gen.cfg.p
@@ -1325,6 +1363,7 @@ def build_all(cfg):
     gp = Gen(cfg, lanes=32, tm=6, signed=True)
     io = {}
     io["p_miller_in"], io["P_FA"] = build_miller_p(gp)
+    io["P_GB"] = build_mulacc_p(gp, io["P_FA"])
     io["miller_in"], io["FA"] = build_miller(gm)
     _, io["FB"], io["GB"] = build_mulacc(gm)
     io["F_FA"], io["OUT"] = build_final_exp(gf)
@@ -1359,7 +1398,9 @@ def verify_all(cfg, gens, io):
     rep["MILLER"], ubm = gm.verify_program("MILLER", {s: p - 1 for s in raw.values()})
     f_ub = max(ubm[FA[k][c]] for k in range(6) for c in range(2))
     rep["P.MILLER"], ubp = gens["P"].verify_program("MILLER", {s: p - 1 for s in io["p_miller_in"].values()})
-    assert max(ubp[io["P_FA"][k][c]] for k in range(6) for c in range(2)) <= 64 * p, "P Miller output exceeds the product-tree input bound"
+    assert max(ubp[io["P_FA"][k][c]] for k in range(6) for c in range(2)) <= TREE_P * p, "P Miller output exceeds the product-tree input bound"
+    rep["P.MULACC"], ubx = gens["P"].verify_program("MULACC", {reg[k][c]: TREE_P * p for reg in (io["P_FA"], io["P_GB"]) for k in range(6) for c in range(2)})
+    assert max(ubx[io["P_FA"][k][c]] for k in range(6) for c in range(2)) <= TREE_P * p, "product-tree invariant (P file)"
     # product trees: operands are Miller outputs or earlier products
     init = {reg[k][c]: 64 * p for reg in (FA, FB, GB) for k in range(6) for c in range(2)}
     assert f_ub <= 64 * p
@@ -1405,7 +1446,7 @@ def emit_tables(path):
                 raw = io["miller_in"] if tag == "M" else io["p_miller_in"]
                 out.append("  static constexpr int IN_XP = %d, IN_YP = %d, IN_XQX = %d, IN_XQY = %d, IN_YQX = %d, IN_YQY = %d;" % tuple(
                     ref(raw[k]) for k in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")))
-                regs_ = (("FA", io["FA"]), ("FB", io["FB"]), ("GB", io["GB"]), ("RAWF", io["RAWF"])) if tag == "M" else (("FA", io["P_FA"]),)
+                regs_ = (("FA", io["FA"]), ("FB", io["FB"]), ("GB", io["GB"]), ("RAWF", io["RAWF"])) if tag == "M" else (("FA", io["P_FA"]), ("GB", io["P_GB"]))
             else:
                 regs_ = (("FA", io["F_FA"]), ("OUT", io["OUT"]))
             for nm, reg in regs_:
