@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -211,20 +212,34 @@ struct MachDev {
     void* blob = nullptr;
 };
 
+// One execution slot: a stream with its own device scratch.  Host-buffer calls take any free slot, so calls made
+// from several host threads (the reference calls PairingProduct from many goroutines, curves/curve.go:132-134)
+// overlap on the GPU: the single-warp final exponentiation of one product runs beside the Miller loops of the next.
+// Device-resident calls are keyed by the caller's stream, so work enqueued on different streams never shares scratch.
+struct Slot {
+    cudaStream_t stream = nullptr;   // the slot's own stream (host-buffer calls)
+    cudaStream_t owner = nullptr;    // caller stream this slot's scratch is currently ordered on (device-resident calls)
+    bool owned = false;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+};
+constexpr int NSLOT = 8;
+
 struct bgls_ctx {
     MachDev mach[2];
+    Slot slots[NSLOT];
+    std::atomic<unsigned> rr{0};
+    std::mutex own_mu;
     bool thread_engine = false;  // BGLS_ENGINE=thread: thread-per-pair kernels only
     bool machine_only = false;   // BGLS_ENGINE=machine: dot-product machine at every size (no hybrid)
     bool miller16 = false;       // BGLS_MILLER=m16: 16-lane Miller program (two pairings per warp) instead of the pipelined one
     int device = 0;
     int sms = 148;
-    cudaStream_t stream = nullptr;
-    void* scratch = nullptr;
-    size_t scratch_bytes = 0;
-    uint64_t launches = 0;
-    bool profiling = false;
+    std::atomic<uint64_t> launches{0};
+    bool profiling = false;      // kernel-time events: single-threaded use only
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before main kernel, between, after finish
-    std::mutex mu;
+    std::mutex err_mu;
     std::string err;
 };
 
@@ -234,6 +249,7 @@ const char* kVersion = "bgls_b200 r1 sm_100a";
 
 int fail(bgls_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
         ctx->err = what;
         if (e != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(e); }
     }
@@ -247,16 +263,16 @@ int fail(bgls_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
 
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-int ensure_scratch(bgls_ctx* ctx, size_t bytes) {
-    if (bytes <= ctx->scratch_bytes) return BGLS_OK;
-    // the old buffer may still be in use by work enqueued earlier
+int ensure_scratch(bgls_ctx* ctx, Slot* sl, size_t bytes) {
+    if (bytes <= sl->scratch_bytes) return BGLS_OK;
+    // the old buffer may still be in use by work enqueued earlier (cudaFree waits for the device)
     CU(cudaDeviceSynchronize());
-    if (ctx->scratch) CU(cudaFree(ctx->scratch));
-    ctx->scratch = nullptr;
-    ctx->scratch_bytes = 0;
+    if (sl->scratch) CU(cudaFree(sl->scratch));
+    sl->scratch = nullptr;
+    sl->scratch_bytes = 0;
     size_t want = align_up(bytes + bytes / 4, 1 << 20);
-    CU(cudaMalloc(&ctx->scratch, want));
-    ctx->scratch_bytes = want;
+    CU(cudaMalloc(&sl->scratch, want));
+    sl->scratch_bytes = want;
     return BGLS_OK;
 }
 int blocks_for(size_t n) {
@@ -574,10 +590,54 @@ size_t pairing_work_bytes(bgls_ctx* ctx, int curve, size_t n) {
     return m > t ? m : t;
 }
 
-struct Guard {
-    bgls_ctx* c;
-    explicit Guard(bgls_ctx* ctx) : c(ctx) { c->mu.lock(); }
-    ~Guard() { c->mu.unlock(); }
+// Acquires an execution slot for the duration of one API call.
+//   host-buffer calls: any free slot (round robin when all are busy), work runs on the slot's own stream;
+//   device-resident calls: the slot ordered on the caller's stream; a slot taken over from another stream first
+//   waits for that stream, so scratch is never shared by work that is not stream-ordered.
+struct SlotLock {
+    Slot* s = nullptr;
+    explicit SlotLock(bgls_ctx* c) {
+        const unsigned start = c->rr.fetch_add(1);
+        for (int i = 0; i < NSLOT && !s; i++) {
+            Slot* t = &c->slots[(start + i) % NSLOT];
+            if (t->mu.try_lock()) s = t;
+        }
+        if (!s) { s = &c->slots[start % NSLOT]; s->mu.lock(); }
+        cudaStream_t prev = nullptr;
+        bool had = false;
+        {
+            std::lock_guard<std::mutex> lk(c->own_mu);
+            had = s->owned;
+            prev = s->owner;
+            s->owned = false;
+        }
+        if (had) cudaStreamSynchronize(prev);
+    }
+    SlotLock(bgls_ctx* c, cudaStream_t user) {
+        {
+            std::lock_guard<std::mutex> lk(c->own_mu);
+            for (int i = 0; i < NSLOT && !s; i++)
+                if (c->slots[i].owned && c->slots[i].owner == user) s = &c->slots[i];
+            for (int i = 0; i < NSLOT && !s; i++)
+                if (!c->slots[i].owned) s = &c->slots[i];
+            if (!s) s = &c->slots[c->rr.fetch_add(1) % NSLOT];
+        }
+        s->mu.lock();
+        cudaStream_t prev = nullptr;
+        bool had = false;
+        {
+            std::lock_guard<std::mutex> lk(c->own_mu);
+            had = s->owned;
+            prev = s->owner;
+            s->owned = true;
+            s->owner = user;
+        }
+        if (had && prev != user) cudaStreamSynchronize(prev);
+        else if (!had) cudaStreamSynchronize(s->stream);
+    }
+    ~SlotLock() { s->mu.unlock(); }
+    SlotLock(const SlotLock&) = delete;
+    SlotLock& operator=(const SlotLock&) = delete;
 };
 
 }  // namespace
@@ -593,7 +653,11 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return BGLS_ERR_NODEV;
     bgls_ctx* ctx = new bgls_ctx();
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    for (int i = 0; ok && i < NSLOT; i++) ok = cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        for (auto& sl : ctx->slots)
+            if (sl.stream) cudaStreamDestroy(sl.stream);
         delete ctx;
         return BGLS_ERR_CUDA;
     }
@@ -617,20 +681,22 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto& sl : ctx->slots) {
+        if (sl.scratch) cudaFree(sl.scratch);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     for (auto& d : ctx->mach)
         if (d.blob) cudaFree(d.blob);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     for (int i = 0; i < 3; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
 }
 const char* bgls_last_error(const bgls_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t bgls_launch_count(const bgls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t bgls_launch_count(const bgls_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int bgls_set_profiling(bgls_ctx* ctx, int on) {
     if (!ctx) return BGLS_ERR_ARG;
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     if (on && !ctx->ev[0])
         for (int i = 0; i < 3; i++) CU(cudaEventCreate(&ctx->ev[i]));
@@ -639,7 +705,7 @@ int bgls_set_profiling(bgls_ctx* ctx, int on) {
 }
 int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish) {
     if (!ctx || !ctx->ev[0] || !ms_main || !ms_finish) return fail(ctx, BGLS_ERR_ARG, "profiling not enabled");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(ctx->ev[2]));
     CU(cudaEventElapsedTime(ms_main, ctx->ev[0], ctx->ev[1]));
@@ -648,21 +714,21 @@ int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish) {
 }
 int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s) {
     if (!ctx || !wide_mac_per_s) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ctx->device));
     const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 8192;
-    int rc = ensure_scratch(ctx, (size_t)blocks * threads * 4);
+    int rc = ensure_scratch(ctx, sl.s, (size_t)blocks * threads * 4);
     if (rc) return rc;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
-        CU(cudaEventRecord(e0, ctx->stream));
-        k_intpipe_peak<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->scratch, 3, iters);
-        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventRecord(e0, sl.s->stream));
+        k_intpipe_peak<<<blocks, threads, 0, sl.s->stream>>>((uint32_t*)sl.s->scratch, 3, iters);
+        CU(cudaEventRecord(e1, sl.s->stream));
         CU(cudaEventSynchronize(e1));
         float ms;
         CU(cudaEventElapsedTime(&ms, e0, e1));
@@ -678,24 +744,24 @@ int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s) {
 static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, int do_final,
                         uint8_t* out, int* flag) {
     if (!ctx || !curve_ok(curve) || !out || (n && (!g1 || !g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(n * 2 * F), b2 = align_up(n * 4 * F), bo = align_up(12 * F + 16);
     const size_t bw = pairing_work_bytes(ctx, curve, n);
-    int rc = ensure_scratch(ctx, b1 + b2 + bo + bw);
+    int rc = ensure_scratch(ctx, sl.s, b1 + b2 + bo + bw);
     if (rc) return rc;
-    uint8_t* base = (uint8_t*)ctx->scratch;
+    uint8_t* base = (uint8_t*)sl.s->scratch;
     uint8_t *d1 = base, *d2 = base + b1, *dout = base + b1 + b2, *work = dout + bo;
     int* dflag = (int*)(dout + 12 * F);
     if (n) {
-        CU(cudaMemcpyAsync(d1, g1, n * 2 * F, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(d2, g2, n * 4 * F, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d1, g1, n * 2 * F, cudaMemcpyHostToDevice, sl.s->stream));
+        CU(cudaMemcpyAsync(d2, g2, n * 4 * F, cudaMemcpyHostToDevice, sl.s->stream));
     }
-    rc = pairing_dev(ctx, curve, d1, d2, n, do_final, dout, dflag, work, ctx->stream);
+    rc = pairing_dev(ctx, curve, d1, d2, n, do_final, dout, dflag, work, sl.s->stream);
     if (rc) return rc;
     uint8_t hbuf[12 * 48 + 16];
-    CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     memcpy(out, hbuf, 12 * F);
     if (flag) memcpy(flag, hbuf + 12 * F, 4);
     return BGLS_OK;
@@ -711,70 +777,70 @@ int bgls_miller_product(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8
 }
 int bgls_final_exp_product(bgls_ctx* ctx, int curve, const uint8_t* partials, size_t k, uint8_t* out_gt, int* is_identity) {
     if (!ctx || !curve_ok(curve) || !out_gt || (k && !partials)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), bi = align_up(k * 12 * F), bo = align_up(12 * F + 16);
-    int rc = ensure_scratch(ctx, bi + bo + mach_work_for(curve, k));
+    int rc = ensure_scratch(ctx, sl.s, bi + bo + mach_work_for(curve, k));
     if (rc) return rc;
-    uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi;
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dout = din + bi;
     int* dflag = (int*)(dout + 12 * F);
-    if (k) CU(cudaMemcpyAsync(din, partials, k * 12 * F, cudaMemcpyHostToDevice, ctx->stream));
-    rc = finish_bytes_dev(ctx, curve, din, k, 1, dout, dflag, dout + bo, ctx->stream);
+    if (k) CU(cudaMemcpyAsync(din, partials, k * 12 * F, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = finish_bytes_dev(ctx, curve, din, k, 1, dout, dflag, dout + bo, sl.s->stream);
     if (rc) return rc;
     uint8_t hbuf[12 * 48 + 16];
-    CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     memcpy(out_gt, hbuf, 12 * F);
     if (is_identity) memcpy(is_identity, hbuf + 12 * F, 4);
     return BGLS_OK;
 }
 int bgls_gt_mul(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* b, uint8_t* out_gt) {
     if (!ctx || !curve_ok(curve) || !a || !b || !out_gt) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), bi = align_up(2 * 12 * F), bo = align_up(12 * F + 16);
-    int rc = ensure_scratch(ctx, bi + bo + mach_work_for(curve, 2));
+    int rc = ensure_scratch(ctx, sl.s, bi + bo + mach_work_for(curve, 2));
     if (rc) return rc;
-    uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi;
-    CU(cudaMemcpyAsync(din, a, 12 * F, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(din + 12 * F, b, 12 * F, cudaMemcpyHostToDevice, ctx->stream));
-    rc = finish_bytes_dev(ctx, curve, din, 2, 0, dout, nullptr, dout + bo, ctx->stream);
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dout = din + bi;
+    CU(cudaMemcpyAsync(din, a, 12 * F, cudaMemcpyHostToDevice, sl.s->stream));
+    CU(cudaMemcpyAsync(din + 12 * F, b, 12 * F, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = finish_bytes_dev(ctx, curve, din, 2, 0, dout, nullptr, dout + bo, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_gt, dout, 12 * F, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(out_gt, dout, 12 * F, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     return BGLS_OK;
 }
 int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out) {
     if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || !pts || !out || n == 0) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t rec = 2 * group * fp_bytes(curve), bi = align_up(n * rec), bo = align_up(rec);
     const size_t bw = align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group));
-    int rc = ensure_scratch(ctx, bi + bo + bw);
+    int rc = ensure_scratch(ctx, sl.s, bi + bo + bw);
     if (rc) return rc;
-    uint8_t *din = (uint8_t*)ctx->scratch, *dout = din + bi, *work = dout + bo;
-    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, ctx->stream));
-    rc = aggregate_dev(ctx, curve, group, din, n, dout, work, ctx->stream);
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dout = din + bi, *work = dout + bo;
+    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = aggregate_dev(ctx, curve, group, din, n, dout, work, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     return BGLS_OK;
 }
 int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out) {
     if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!pts || !scalars || !out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
     if (n == 0) return BGLS_OK;
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t rec = 2 * group * fp_bytes(curve), bi = align_up(n * rec), bs = align_up(n * 32);
-    int rc = ensure_scratch(ctx, 2 * bi + bs);
+    int rc = ensure_scratch(ctx, sl.s, 2 * bi + bs);
     if (rc) return rc;
-    uint8_t *din = (uint8_t*)ctx->scratch, *dsc = din + bi, *dout = dsc + bs;
-    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dsc, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    rc = scale_dev(ctx, curve, group, din, dsc, n, dout, ctx->stream);
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dsc = din + bi, *dout = dsc + bs;
+    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, sl.s->stream));
+    CU(cudaMemcpyAsync(dsc, scalars, n * 32, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = scale_dev(ctx, curve, group, din, dsc, n, dout, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out, dout, n * rec, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(out, dout, n * rec, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     return BGLS_OK;
 }
 static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_off, size_t n, void* d_out, cudaStream_t s) {
@@ -793,25 +859,24 @@ int bgls_hash_to_g1(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_
         if (offsets[i + 1] < offsets[i]) return fail(ctx, BGLS_ERR_ARG, "offsets not monotone");
     const size_t total = offsets[n] - offsets[0];
     if (total && !msgs) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), bm = align_up(total + 16), bo = align_up((n + 1) * 8), bp = align_up(n * 2 * F);
-    int rc = ensure_scratch(ctx, bm + bo + bp);
+    int rc = ensure_scratch(ctx, sl.s, bm + bo + bp);
     if (rc) return rc;
-    uint8_t *dm = (uint8_t*)ctx->scratch, *doff = dm + bm, *dout = doff + bo;
+    uint8_t *dm = (uint8_t*)sl.s->scratch, *doff = dm + bm, *dout = doff + bo;
     std::vector<uint64_t> rel(n + 1);
     for (size_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
-    if (total) CU(cudaMemcpyAsync(dm, msgs + offsets[0], total, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(doff, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = hash_dev(ctx, curve, dm, doff, n, dout, ctx->stream);
+    if (total) CU(cudaMemcpyAsync(dm, msgs + offsets[0], total, cudaMemcpyHostToDevice, sl.s->stream));
+    CU(cudaMemcpyAsync(doff, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = hash_dev(ctx, curve, dm, doff, n, dout, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out, dout, n * 2 * F, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(out, dout, n * 2 * F, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     return BGLS_OK;
 }
 int bgls_hash_to_g1_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_offsets, size_t n, void* d_out, void* stream) {
     if (!ctx || !curve_ok(curve) || (n && (!d_offsets || !d_out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     return hash_dev(ctx, curve, d_msgs, d_offsets, n, d_out, (cudaStream_t)stream);
 }
@@ -824,85 +889,84 @@ int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const 
     if (offsets[0] != 0) return fail(ctx, BGLS_ERR_ARG, "offsets[0] must be 0");
     const size_t total = offsets[nbatch];
     if (total && (!g1 || !g2)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(total * 2 * F), b2 = align_up(total * 4 * F);
     const size_t bf = align_up((nbatch + 1) * 8), bk = align_up(nbatch);
     const size_t bw = std::max(align_up(total * fp12_dev_bytes(curve)), mach_work_for(curve, total + nbatch));
-    int rc = ensure_scratch(ctx, b1 + b2 + bf + bk + bw);
+    int rc = ensure_scratch(ctx, sl.s, b1 + b2 + bf + bk + bw);
     if (rc) return rc;
-    uint8_t *d1 = (uint8_t*)ctx->scratch, *d2 = d1 + b1, *doff = d2 + b2, *dok = doff + bf, *work = dok + bk;
+    uint8_t *d1 = (uint8_t*)sl.s->scratch, *d2 = d1 + b1, *doff = d2 + b2, *dok = doff + bf, *work = dok + bk;
     if (total) {
-        CU(cudaMemcpyAsync(d1, g1, total * 2 * F, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(d2, g2, total * 4 * F, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d1, g1, total * 2 * F, cudaMemcpyHostToDevice, sl.s->stream));
+        CU(cudaMemcpyAsync(d2, g2, total * 4 * F, cudaMemcpyHostToDevice, sl.s->stream));
     }
-    CU(cudaMemcpyAsync(doff, offsets, (nbatch + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = batch_dev(ctx, curve, d1, d2, doff, nbatch, total, dok, work, ctx->stream);
+    CU(cudaMemcpyAsync(doff, offsets, (nbatch + 1) * 8, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = batch_dev(ctx, curve, d1, d2, doff, nbatch, total, dok, work, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_ok, dok, nbatch, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(out_ok, dok, nbatch, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
     return BGLS_OK;
 }
 
 // ---- device-resident entry points (no synchronisation)
-static int dev_work(bgls_ctx* ctx, size_t bytes, void** work) {
-    int rc = ensure_scratch(ctx, bytes);
+static int dev_work(bgls_ctx* ctx, Slot* sl, size_t bytes, void** work) {
+    int rc = ensure_scratch(ctx, sl, bytes);
     if (rc) return rc;
-    *work = ctx->scratch;
+    *work = sl->scratch;
     return BGLS_OK;
 }
 int bgls_pairing_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, void* d_out_gt,
                              void* d_is_identity, void* stream) {
     if (!ctx || !curve_ok(curve) || !d_out_gt || (n && (!d_g1 || !d_g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, pairing_work_bytes(ctx, curve, n), &work);
+    int rc = dev_work(ctx, sl.s, pairing_work_bytes(ctx, curve, n), &work);
     if (rc) return rc;
     return pairing_dev(ctx, curve, d_g1, d_g2, n, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
 }
 int bgls_miller_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, void* d_out_f, void* stream) {
     if (!ctx || !curve_ok(curve) || !d_out_f || (n && (!d_g1 || !d_g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, pairing_work_bytes(ctx, curve, n), &work);
+    int rc = dev_work(ctx, sl.s, pairing_work_bytes(ctx, curve, n), &work);
     if (rc) return rc;
     return pairing_dev(ctx, curve, d_g1, d_g2, n, 0, d_out_f, nullptr, work, (cudaStream_t)stream);
 }
 int bgls_final_exp_product_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, void* d_out_gt,
                                void* d_is_identity, void* stream) {
     if (!ctx || !curve_ok(curve) || !d_out_gt || (k && !d_partials)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, mach_work_for(curve, k), &work);
+    int rc = dev_work(ctx, sl.s, mach_work_for(curve, k), &work);
     if (rc) return rc;
     return finish_bytes_dev(ctx, curve, d_partials, k, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
 }
 int bgls_aggregate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* stream) {
     if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || !d_pts || !d_out || n == 0) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group)), &work);
+    int rc = dev_work(ctx, sl.s, align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group)), &work);
     if (rc) return rc;
     return aggregate_dev(ctx, curve, group, d_pts, n, d_out, work, (cudaStream_t)stream);
 }
 int bgls_scale_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void* d_scalars, size_t n,
                           void* d_out, void* stream) {
     if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!d_pts || !d_scalars || !d_out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
     CU(cudaSetDevice(ctx->device));
     return scale_dev(ctx, curve, group, d_pts, d_scalars, n, d_out, (cudaStream_t)stream);
 }
 int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_offsets,
                                  size_t nbatch, size_t total_pairs, void* d_out_ok, void* stream) {
     if (!ctx || !curve_ok(curve) || !d_offsets || (nbatch && !d_out_ok) || (total_pairs && (!d_g1 || !d_g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    Guard g(ctx);
+    SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, std::max(align_up(total_pairs * fp12_dev_bytes(curve)), mach_work_for(curve, total_pairs + nbatch)), &work);
+    int rc = dev_work(ctx, sl.s, std::max(align_up(total_pairs * fp12_dev_bytes(curve)), mach_work_for(curve, total_pairs + nbatch)), &work);
     if (rc) return rc;
     return batch_dev(ctx, curve, d_g1, d_g2, d_offsets, nbatch, total_pairs, d_out_ok, work, (cudaStream_t)stream);
 }

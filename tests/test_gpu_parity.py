@@ -255,3 +255,37 @@ def test_scheme_layer_end_to_end():
         assert gt is None and not ok      # length mismatch (curves/curve.go:126-128)
         assert curve.Pair(curve.GetG2(), curve.GetG2()) == (None, False)   # type mismatch (curves/altbn128.go:131-140)
         assert curve.Pair(curve.GetG1(), curve.GetG2Infinity())[0].Equals(curve.GetGTIdentity())
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_concurrent_calls_from_host_threads(ctx, cid, c):
+    """PairingProduct is called from many goroutines in the reference (curves/curve.go:132-134): concurrent
+    host-buffer calls on one context run on separate execution slots and must return the same bytes as the
+    serial calls, for products of different sizes in flight at the same time."""
+    import threading
+    rng = random.Random(77 + cid)
+    cases = []
+    for n in (1, 3, 8, 17, 40, 64):
+        g1, _ = rand_points(cid, c, 1, n, rng)
+        g2, _ = rand_points(cid, c, 2, n, rng)
+        cases.append((g1, g2, n, C.pairing_product(cid, g1, g2, n, 4, 0)))
+    agg1, agg2 = make_aggregate(cid, c, 12, rng)
+    errors = []
+
+    def work(tid):
+        try:
+            for rep in range(6):
+                g1, g2, n, want = cases[(tid + rep) % len(cases)]
+                gt, ok = ctx.pairing_product(cid, g1, g2, n)
+                assert gt == want and not ok
+                gt, ok = ctx.pairing_product(cid, agg1, agg2, 13)
+                assert ok
+                assert ctx.aggregate_points(cid, 2, g2, n) == C.aggregate(cid, 2, g2, n, 2)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
