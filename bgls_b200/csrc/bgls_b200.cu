@@ -67,6 +67,40 @@ __global__ void __launch_bounds__(TB) k_miller_product(const uint8_t* __restrict
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// Throughput variant: every thread carries K consecutive pairs through one shared Miller accumulator
+// (miller_loop_shared): one Fp12 squaring per iteration for K pairs.
+constexpr int MSHARE = 4;
+constexpr size_t MSHARED_MIN = 32768;   // pairs: below this one pair per thread keeps more warps busy
+template <class C, int K>
+__global__ void __launch_bounds__(TB) k_miller_product_shared(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                              size_t n, Fp12<C>* __restrict__ partial) {
+    __shared__ Fp12<C> sh[TB];
+    Fp12<C> acc;
+    fp12_one(acc);
+    bool first = true;
+    const size_t groups = (n + K - 1) / K;
+    for (size_t g = (size_t)blockIdx.x * TB + threadIdx.x; g < groups; g += (size_t)gridDim.x * TB) {
+        G1Aff<C> P[K];
+        G2Aff<C> Q[K];
+        const size_t base = g * K;
+        const int k = (int)(n - base < (size_t)K ? n - base : (size_t)K);
+        for (int j = 0; j < k; j++) {
+            g1_load<C>(P[j], g1 + (base + j) * 2 * C::FP_BYTES);
+            g2_load<C>(Q[j], g2 + (base + j) * 4 * C::FP_BYTES);
+        }
+        if (first) {
+            miller_loop_shared<C, K>(acc, P, Q, k);
+            first = false;
+        } else {
+            Fp12<C> f;
+            miller_loop_shared<C, K>(f, P, Q, k);
+            fp12_mul(acc, acc, f);
+        }
+    }
+    block_product(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 // one block: multiply k partial values, optionally exponentiate, emit wire bytes + identity flag
 template <class C, bool IN_BYTES>
 __global__ void __launch_bounds__(TB) k_finish(const void* __restrict__ in, size_t k, int do_final,
@@ -233,6 +267,7 @@ struct bgls_ctx {
     std::mutex own_mu;
     bool thread_engine = false;  // BGLS_ENGINE=thread: thread-per-pair kernels only
     bool machine_only = false;   // BGLS_ENGINE=machine: dot-product machine at every size (no hybrid)
+    bool no_shared = false;      // BGLS_MILLER=noshare: thread engine without the shared Miller accumulator (one pair per thread)
     bool miller16 = false;       // BGLS_MILLER=m16: 16-lane Miller program (two pairings per warp) instead of the pipelined one
     int device = 0;
     int sms = 148;
@@ -294,14 +329,20 @@ template <class C>
 int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final, uint8_t* d_out,
                     int* d_flag, void* work, cudaStream_t s) {
     const int nb = blocks_for(n);
+    int nb_used = nb;
     Fp12<C>* partial = (Fp12<C>*)work;
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
-    if (n > 0) {
+    if (n >= MSHARED_MIN && !ctx->no_shared) {
+        const int nbs = blocks_for((n + MSHARE - 1) / MSHARE);
+        k_miller_product_shared<C, MSHARE><<<nbs, TB, 0, s>>>(d_g1, d_g2, n, partial);
+        ctx->launches++;
+        nb_used = nbs;
+    } else if (n > 0) {
         k_miller_product<C><<<nb, TB, 0, s>>>(d_g1, d_g2, n, partial);
         ctx->launches++;
     }
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
-    k_finish<C, false><<<1, TB, 0, s>>>(partial, n > 0 ? (size_t)nb : 0, do_final, d_out, d_flag);
+    k_finish<C, false><<<1, TB, 0, s>>>(partial, n > 0 ? (size_t)nb_used : 0, do_final, d_out, d_flag);
     ctx->launches++;
     if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
     CU(cudaGetLastError());
@@ -666,6 +707,7 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     ctx->machine_only = eng && std::string(eng) == "machine";
     const char* mil = getenv("BGLS_MILLER");
     ctx->miller16 = mil && std::string(mil) == "m16";
+    ctx->no_shared = mil && std::string(mil) == "noshare";
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
     if (ctx->sms <= 0) ctx->sms = 148;
     int rc = upload_mach<mtab::BN254_M, mtab::BN254_M_T, mtab::BN254_F, mtab::BN254_F_T, mtab::BN254_MP, mtab::BN254_MP_T>(ctx, ctx->mach[0]);

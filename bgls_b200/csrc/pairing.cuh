@@ -162,6 +162,50 @@ template <class C> HDNI void miller_loop(Fp12<C>& f, const G1Aff<C>& P, const G2
     }
 }
 
+// Product of the Miller functions of k <= K pairs with ONE shared accumulator: prod_j f_{lambda,Q_j}(P_j).
+// Every iteration squares f once and multiplies the k lines into it, instead of k squarings (the squaring is
+// 36 of the 102 Fp multiplications of a doubling iteration).  Pairs with a point at infinity contribute 1.
+template <class C, int K> HDNI void miller_loop_shared(Fp12<C>& f, const G1Aff<C>* P, const G2Aff<C>* Q, int k) {
+    fp12_one(f);
+    G2Proj<C> T[K];
+    bool any = false;
+    for (int j = 0; j < k; j++) {
+        T[j].X = Q[j].x;
+        T[j].Y = Q[j].y;
+        fp2_one(T[j].Z);
+        any = any || !(P[j].inf || Q[j].inf);
+    }
+    if (!any) return;
+    for (int i = C::LOOP_TOP - 1; i >= 0; i--) {
+        if (i != C::LOOP_TOP - 1) fp12_sqr(f, f);  // f == 1 on the first pass
+        const bool bit = (C::LOOP_LO >> i) & 1;
+        for (int j = 0; j < k; j++) {
+            if (P[j].inf || Q[j].inf) continue;
+            dbl_step(f, T[j], P[j]);
+            if (bit) add_step(f, T[j], Q[j], P[j]);
+        }
+    }
+    if (C::IS_BN) {
+        Fp2<C> g2, g3, t;
+        fp2_set(g2, C::GAMMA1(2));
+        fp2_set(g3, C::GAMMA1(3));
+        for (int j = 0; j < k; j++) {
+            if (P[j].inf || Q[j].inf) continue;
+            G2Aff<C> Q1, Q2;
+            Q1.inf = Q2.inf = false;
+            fp2_conj(t, Q[j].x); fp2_mul(Q1.x, t, g2);
+            fp2_conj(t, Q[j].y); fp2_mul(Q1.y, t, g3);
+            fp2_conj(t, Q1.x); fp2_mul(Q2.x, t, g2);
+            fp2_conj(t, Q1.y); fp2_mul(Q2.y, t, g3);
+            fp2_neg(Q2.y, Q2.y);
+            add_step(f, T[j], Q1, P[j]);
+            add_step(f, T[j], Q2, P[j]);
+        }
+    } else {
+        fp12_conj(f, f);  // x < 0
+    }
+}
+
 // ---------------------------------------------------------------- final exponentiation
 template <class C> HDNI void final_exp(Fp12<C>& r, const Fp12<C>& f) {
     Fp12<C> m, t0, t1;

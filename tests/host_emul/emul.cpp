@@ -21,6 +21,23 @@ template <class C> static int pairing_product(const uint8_t* g1, const uint8_t* 
     fp12_to_be<C>(out, acc);
     return fp12_is_one(acc) ? 1 : 0;
 }
+template <class C, int K> static int pairing_product_shared(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final) {
+    Fp12<C> acc;
+    fp12_one(acc);
+    for (size_t base = 0; base < n; base += K) {
+        G1Aff<C> P[K]; G2Aff<C> Q[K]; Fp12<C> f;
+        const int k = (int)(n - base < (size_t)K ? n - base : (size_t)K);
+        for (int j = 0; j < k; j++) {
+            g1_load<C>(P[j], g1 + (base + j) * 2 * C::FP_BYTES);
+            g2_load<C>(Q[j], g2 + (base + j) * 4 * C::FP_BYTES);
+        }
+        miller_loop_shared<C, K>(f, P, Q, k);
+        fp12_mul(acc, acc, f);
+    }
+    if (do_final) final_exp(acc, acc);
+    fp12_to_be<C>(out, acc);
+    return fp12_is_one(acc) ? 1 : 0;
+}
 template <class C, class F> static void aggregate(const uint8_t* pts, size_t n, size_t rec, uint8_t* out) {
     Jac<F> acc; acc.inf = true;
     for (size_t i = 0; i < n; i++) { Jac<F> p; jac_load<C>(p, pts + i * rec); jac_add(acc, acc, p); }
@@ -42,6 +59,9 @@ template <class C> static void fpmul(const uint8_t* a, const uint8_t* b, uint8_t
 extern "C" {
 int emu_pairing_product(int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final) {
     return curve == 0 ? pairing_product<BN254>(g1, g2, n, out, do_final) : pairing_product<BLS381>(g1, g2, n, out, do_final);
+}
+int emu_pairing_product_shared(int curve, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* out, int do_final) {
+    return curve == 0 ? pairing_product_shared<BN254, 4>(g1, g2, n, out, do_final) : pairing_product_shared<BLS381, 4>(g1, g2, n, out, do_final);
 }
 void emu_aggregate(int curve, int group, const uint8_t* pts, size_t n, uint8_t* out) {
     if (curve == 0) { if (group == 1) aggregate<BN254, Fp<BN254>>(pts, n, 64, out); else aggregate<BN254, Fp2<BN254>>(pts, n, 128, out); }

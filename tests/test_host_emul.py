@@ -61,6 +61,16 @@ def test_thread_engine_templates(E, cid, c):
     assert out.raw.hex() == g["product_gt"]
     E.emu_pairing_product(cid, g1, g2, n, out, 0)
     assert out.raw == C.miller_product(cid, g1, g2, n)  # same formulas as the C oracle: raw values agree too
+    # shared Miller accumulator (K = 4 pairs per thread, ragged tail, an infinity pair in the middle)
+    E.emu_pairing_product_shared.argtypes = E.emu_pairing_product.argtypes
+    E.emu_pairing_product_shared(cid, g1, g2, n, out, 1)
+    assert out.raw.hex() == g["product_gt"]
+    G1 = g1[:2 * nb] + c.marshal_g1(None) + g1[2 * nb:]
+    G2 = g2[:4 * nb] + c.marshal_g2(c.g2) + g2[4 * nb:]
+    E.emu_pairing_product_shared(cid, G1, G2, n + 1, out, 1)
+    assert out.raw.hex() == g["product_gt"]
+    E.emu_pairing_product_shared(cid, g1, g2, n, out, 0)
+    assert C.fp12_product(cid, out.raw, 1, True).hex() == g["product_gt"]
     rng = random.Random(8)
     for grp, key in ((1, "g1"), (2, "g2")):
         blob = bytes.fromhex(g[key])
