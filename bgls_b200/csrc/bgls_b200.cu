@@ -101,6 +101,53 @@ __global__ void __launch_bounds__(TB) k_miller_product_shared(const uint8_t* __r
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// Batch of independent products (throughput mode): one block per check, every thread carries up to KB_MAX pairs of
+// the check through one shared Miller accumulator; the block product leaves the check's raw Miller product as wire bytes.
+constexpr int TBB = 64;
+constexpr int KB_MAX = 8;
+template <class C>
+__global__ void __launch_bounds__(TBB) k_miller_batch_shared(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                            const unsigned long long* __restrict__ off, size_t nbatch,
+                                                            uint8_t* __restrict__ raw) {
+    __shared__ Fp12<C> sh[TBB];
+    const size_t b = blockIdx.x;
+    const size_t lo = off[b], hi = off[b + 1];
+    size_t k = (hi - lo + TBB - 1) / TBB;
+    if (k > (size_t)KB_MAX) k = KB_MAX;
+    if (k == 0) k = 1;
+    Fp12<C> acc;
+    fp12_one(acc);
+    bool first = true;
+    for (size_t base = lo + (size_t)threadIdx.x * k; base < hi; base += (size_t)TBB * k) {
+        G1Aff<C> P[KB_MAX];
+        G2Aff<C> Q[KB_MAX];
+        const int kk = (int)(hi - base < k ? hi - base : k);
+        for (int j = 0; j < kk; j++) {
+            g1_load<C>(P[j], g1 + (base + j) * 2 * C::FP_BYTES);
+            g2_load<C>(Q[j], g2 + (base + j) * 4 * C::FP_BYTES);
+        }
+        if (first) {
+            miller_loop_shared<C, KB_MAX>(acc, P, Q, kk);
+            first = false;
+        } else {
+            Fp12<C> f;
+            miller_loop_shared<C, KB_MAX>(f, P, Q, kk);
+            fp12_mul(acc, acc, f);
+        }
+    }
+    const int tid = threadIdx.x;
+    sh[tid] = acc;
+    __syncthreads();
+    for (int s = TBB / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            fp12_mul(acc, acc, sh[tid + s]);
+            sh[tid] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) fp12_to_be<C>(raw + b * 12 * C::FP_BYTES, acc);
+}
+
 // one block: multiply k partial values, optionally exponentiate, emit wire bytes + identity flag
 template <class C, bool IN_BYTES>
 __global__ void __launch_bounds__(TB) k_finish(const void* __restrict__ in, size_t k, int do_final,
@@ -170,6 +217,26 @@ __global__ void __launch_bounds__(TB) k_aggregate(const uint8_t* __restrict__ pt
         __syncthreads();
     }
     if (tid == 0) partial[blockIdx.x] = acc;
+}
+// one level of the partial-sum tree: TB Jacobian partials per block -> one
+template <class F>
+__global__ void __launch_bounds__(TB) k_aggregate_level(const Jac<F>* __restrict__ in, size_t k, Jac<F>* __restrict__ out) {
+    __shared__ Jac<F> sh[TB];
+    const int tid = threadIdx.x;
+    const size_t i = (size_t)blockIdx.x * TB + tid;
+    Jac<F> acc;
+    if (i < k) acc = in[i];
+    else acc.inf = true;
+    sh[tid] = acc;
+    __syncthreads();
+    for (int s = TB / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            jac_add(acc, acc, sh[tid + s]);
+            sh[tid] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[blockIdx.x] = acc;
 }
 template <class C, class F>
 __global__ void __launch_bounds__(TB) k_aggregate_finish(const Jac<F>* __restrict__ partial, size_t k, uint8_t* __restrict__ out) {
@@ -316,6 +383,9 @@ int blocks_for(size_t n) {
     if (b > (size_t)MAX_BLOCKS) b = MAX_BLOCKS;
     return (int)b;
 }
+size_t jac_dev_bytes(int c, int g);
+// scratch of the aggregation pipeline: block partials + the second buffer of the level tree
+size_t agg_work_bytes(int curve, int group, size_t n);
 bool curve_ok(int c) { return c == BGLS_ALTBN128 || c == BGLS_BLS12_381; }
 size_t fp_bytes(int c) { return c == BGLS_ALTBN128 ? 32 : 48; }
 size_t fp12_dev_bytes(int c) { return c == BGLS_ALTBN128 ? sizeof(Fp12<BN254>) : sizeof(Fp12<BLS381>); }
@@ -325,6 +395,10 @@ size_t jac_dev_bytes(int c, int g) {
 }
 
 // ---- enqueue helpers (device pointers); `work` is device scratch owned by the caller
+size_t agg_work_bytes(int curve, int group, size_t n) {
+    const size_t nb = (size_t)blocks_for(n);
+    return align_up((nb + nb / TB + 2) * jac_dev_bytes(curve, group));
+}
 template <class C>
 int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final, uint8_t* d_out,
                     int* d_flag, void* work, cudaStream_t s) {
@@ -352,9 +426,19 @@ template <class C, class F>
 int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, size_t rec, uint8_t* d_out, void* work, cudaStream_t s) {
     const int nb = blocks_for(n);
     Jac<F>* partial = (Jac<F>*)work;
+    Jac<F>* other = partial + nb;   // second buffer of the level tree (agg_work_bytes)
     k_aggregate<C, F><<<nb, TB, 0, s>>>(d_pts, n, rec, partial);
-    k_aggregate_finish<C, F><<<1, TB, 0, s>>>(partial, nb, d_out);
-    ctx->launches += 2;
+    ctx->launches++;
+    size_t k = (size_t)nb;
+    while (k > (size_t)TB) {   // log-depth tree over the block partials instead of one block walking all of them
+        const size_t nk = (k + TB - 1) / TB;
+        k_aggregate_level<F><<<(unsigned)nk, TB, 0, s>>>(partial, k, other);
+        ctx->launches++;
+        std::swap(partial, other);
+        k = nk;
+    }
+    k_aggregate_finish<C, F><<<1, TB, 0, s>>>(partial, k, d_out);
+    ctx->launches++;
     CU(cudaGetLastError());
     return BGLS_OK;
 }
@@ -467,6 +551,11 @@ constexpr size_t MHYBRID = 16384;  // pairs: above this the thread-per-pair Mill
 constexpr size_t MSMALL = 0;  // GPW=1 threshold: measured slower on B200 (1.55 ms vs 1.19 ms at 1025 pairs: the IMAD pipe is
                               // charged per warp instruction, so half-empty warps double the pipe work); kept for experiments
 
+template <class M> struct CurveOf;
+template <> struct CurveOf<mtab::BN254_M> { using type = BN254; };
+template <> struct CurveOf<mtab::BLS381_M> { using type = BLS381; };
+constexpr size_t MBATCH_SHARED_MIN = 8192;   // total pairs of a batch from which the shared-accumulator thread kernel is used
+
 template <class M> struct PFile;
 template <> struct PFile<mtab::BN254_M> { using type = mtab::BN254_MP; };
 template <> struct PFile<mtab::BLS381_M> { using type = mtab::BLS381_MP; };
@@ -572,6 +661,18 @@ int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8
                size_t total, uint8_t* d_ok, void* work, cudaStream_t s) {
     uint32_t* buf0 = (uint32_t*)work;
     uint32_t* buf1 = (uint32_t*)((char*)work + align_up((total + 2) * mach_val_bytes<M>()));
+    if (total >= MBATCH_SHARED_MIN && total >= 16 * nbatch && !ctx->no_shared && !ctx->machine_only) {
+        // throughput regime: saturated-limb thread kernel with a shared Miller accumulator per thread, one block per
+        // check -> raw products as wire bytes -> machine form -> one final exponentiation (one warp) per check
+        using C = typename CurveOf<M>::type;
+        uint8_t* raw = (uint8_t*)buf1;
+        k_miller_batch_shared<C><<<(unsigned)nbatch, TBB, 0, s>>>(d_g1, d_g2, d_off, nbatch, raw);
+        k_mach_import<M><<<(unsigned)((nbatch + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.import_a, M::IMPORT_A_LEN, raw, nbatch, buf0);
+        k_mach_finish<F, M><<<(unsigned)nbatch, MFIN_THREADS, mach_smem_bytes<F>(1), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf0, nbatch, nullptr, nullptr, d_ok);
+        ctx->launches += 3;
+        CU(cudaGetLastError());
+        return BGLS_OK;
+    }
     launch_miller<M>(ctx, d, d_g1, d_g2, total, buf0, s);
     k_mach_reduce<M><<<(unsigned)((nbatch + MGPB - 1) / MGPB), MWPB * 32, mach_smem_bytes<M>(MGPB), s>>>(d.m, d.mul_ab, d.mul_ba, buf0, total, 0, d_off, nbatch, buf1);
     k_mach_finish<F, M><<<(unsigned)nbatch, MFIN_THREADS, mach_smem_bytes<F>(1), s>>>(d.f, d.finalexp, F::FINALEXP_LEN, buf1, nbatch, nullptr, nullptr, d_ok);
@@ -857,7 +958,7 @@ int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pt
     SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t rec = 2 * group * fp_bytes(curve), bi = align_up(n * rec), bo = align_up(rec);
-    const size_t bw = align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group));
+    const size_t bw = agg_work_bytes(curve, group, n);
     int rc = ensure_scratch(ctx, sl.s, bi + bo + bw);
     if (rc) return rc;
     uint8_t *din = (uint8_t*)sl.s->scratch, *dout = din + bi, *work = dout + bo;
@@ -992,7 +1093,7 @@ int bgls_aggregate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d
     SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, sl.s, align_up((size_t)blocks_for(n) * jac_dev_bytes(curve, group)), &work);
+    int rc = dev_work(ctx, sl.s, agg_work_bytes(curve, group, n), &work);
     if (rc) return rc;
     return aggregate_dev(ctx, curve, group, d_pts, n, d_out, work, (cudaStream_t)stream);
 }

@@ -97,3 +97,26 @@ def test_config5_batch_of_independent_verifies(ctx):
         offsets.append(offsets[-1] + signers + 1)
         expect.append(good)
     assert ctx.pairing_check_batch(cid, b"".join(G1), b"".join(G2), offsets) == expect
+
+
+def test_batch_shared_accumulator_ragged(ctx):
+    """Throughput path of pairing_check_batch (one block per check, shared Miller accumulators): ragged check
+    sizes around the per-thread grouping boundaries, valid and corrupted, against per-check PairingProduct."""
+    cid, c = CURVES[0]
+    nb = c.nbytes
+    rng = random.Random(91)
+    sizes = [16, 17, 63, 64, 65, 127, 128, 129, 200, 257, 511, 512, 513, 600, 40, 33] * 3
+    G1, G2, offsets, expect = [], [], [0], []
+    for i, n in enumerate(sizes):
+        g1, g2 = synth_aggregate(ctx, cid, c, n - 1, 500 + n + 1000 * (i // 16))
+        good = i % 3 != 1
+        if not good:   # swap two hashes: still on the curve, product no longer 1
+            g1 = g1[2 * nb:4 * nb] + g1[:2 * nb] + g1[4 * nb:] if n > 2 else g1[:-2 * nb] + c.marshal_g1(c.g1)
+        _, ok = ctx.pairing_product(cid, g1, g2, n)
+        assert ok == good
+        G1.append(g1)
+        G2.append(g2)
+        offsets.append(offsets[-1] + n)
+        expect.append(good)
+    assert offsets[-1] >= 8192
+    assert ctx.pairing_check_batch(cid, b"".join(G1), b"".join(G2), offsets) == expect
