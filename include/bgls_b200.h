@@ -23,8 +23,13 @@
  *   - host-buffer entry points copy in, run on the context's stream and synchronise before
  *     returning.  `_dev` entry points take device pointers (16-byte aligned) and a cudaStream_t
  *     (as void*), enqueue the work and return without synchronising.
- *   - a context is bound to one CUDA device and is internally serialised (safe to share between
- *     threads / goroutines; calls on one context do not run concurrently).
+ *   - a context is bound to one CUDA device and is safe to share between threads / goroutines (the
+ *     reference calls Pair / PairingProduct from many goroutines, curves/curve.go:132-134).  It owns
+ *     8 execution slots (stream + device scratch each): concurrent host-buffer calls run on different
+ *     slots and overlap on the GPU -- the single-warp final exponentiation of one product beside the
+ *     Miller loops of the next.  `_dev` calls are keyed by the caller's stream: work enqueued on
+ *     different streams uses different scratch; more than 8 streams in flight are serialised.
+ *     bgls_last_error() returns the text of the most recent failing call on the context.
  */
 #ifndef BGLS_B200_H
 #define BGLS_B200_H
