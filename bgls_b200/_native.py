@@ -19,6 +19,7 @@ EXPORTS = [
     "bgls_gt_mul", "bgls_aggregate_points", "bgls_scale_points", "bgls_miller_product", "bgls_final_exp_product",
     "bgls_pairing_check_batch", "bgls_pairing_product_dev", "bgls_miller_product_dev", "bgls_final_exp_product_dev",
     "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_hash_to_g1", "bgls_hash_to_g1_dev", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
+    "bgls_compress_points", "bgls_compress_points_dev", "bgls_decompress_points", "bgls_decompress_points_dev",
 ]
 
 _lib = None
@@ -59,6 +60,10 @@ def load():
     L.bgls_pairing_check_batch_dev.argtypes = [vp, i, vp, vp, vp, sz, sz, vp, vp]
     L.bgls_hash_to_g1.argtypes = [vp, i, cp, ctypes.POINTER(ctypes.c_uint64), sz, cp]
     L.bgls_hash_to_g1_dev.argtypes = [vp, i, vp, vp, sz, vp, vp]
+    L.bgls_compress_points.argtypes = [vp, i, i, cp, sz, cp]
+    L.bgls_compress_points_dev.argtypes = [vp, i, i, vp, sz, vp, vp]
+    L.bgls_decompress_points.argtypes = [vp, i, i, cp, sz, i, cp, cp]
+    L.bgls_decompress_points_dev.argtypes = [vp, i, i, vp, sz, i, vp, vp, vp]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
     L.bgls_set_profiling.argtypes = [vp, i]
@@ -141,6 +146,19 @@ class Context:
         out = ctypes.create_string_buffer(max(1, n * 2 * group * FP_BYTES[curve]))
         self._chk(self._L.bgls_scale_points(self._h, curve, group, pts, scalars, n, out))
         return out.raw[: n * 2 * group * FP_BYTES[curve]]
+
+    def compress_points(self, curve, group, pts: bytes, n: int) -> bytes:
+        """n uncompressed records -> n compressed records (Point.Marshal)."""
+        out = ctypes.create_string_buffer(max(1, n * group * FP_BYTES[curve]))
+        self._chk(self._L.bgls_compress_points(self._h, curve, group, pts, n, out))
+        return out.raw[: n * group * FP_BYTES[curve]]
+
+    def decompress_points(self, curve, group, data: bytes, n: int, check_subgroup: bool = False):
+        """n compressed records -> (n uncompressed records, list of ok flags) (UnmarshalG1 / UnmarshalG2)."""
+        out = ctypes.create_string_buffer(max(1, n * 2 * group * FP_BYTES[curve]))
+        ok = ctypes.create_string_buffer(max(1, n))
+        self._chk(self._L.bgls_decompress_points(self._h, curve, group, data, n, 1 if check_subgroup else 0, out, ok))
+        return out.raw[: n * 2 * group * FP_BYTES[curve]], [bool(b) for b in ok.raw[:n]]
 
     def miller_product(self, curve, g1: bytes, g2: bytes, n: int) -> bytes:
         out = ctypes.create_string_buffer(12 * FP_BYTES[curve])

@@ -22,6 +22,7 @@
 #include "pairing.cuh"
 #include "machine_kernels.cuh"
 #include "hash.cuh"
+#include "codec.cuh"
 
 namespace bgls {
 
@@ -277,6 +278,27 @@ __global__ void __launch_bounds__(TB) k_hash_to_g1(const uint8_t* __restrict__ m
     const size_t len = (size_t)(off[i + 1] - off[i]);
     if constexpr (C::IS_BN) hash_to_g1_keccak_ti<C>(out + i * 2 * C::FP_BYTES, m, len);
     else hash_to_g1_ft<C>(out + i * 2 * C::FP_BYTES, m, len);
+}
+
+// compressed wire formats, one point per thread (codec.cuh)
+template <class C, int G>
+__global__ void __launch_bounds__(TB) k_compress(const uint8_t* __restrict__ pts, size_t n, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    constexpr int F = C::FP_BYTES;
+    if (G == 1) compress_g1<C>(out + i * F, pts + i * 2 * F);
+    else compress_g2<C>(out + i * 2 * F, pts + i * 4 * F);
+}
+template <class C, int G>
+__global__ void __launch_bounds__(TB) k_decompress(const uint8_t* __restrict__ in, size_t n, int check_subgroup,
+                                                   uint8_t* __restrict__ pts, uint8_t* __restrict__ ok) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    constexpr int F = C::FP_BYTES;
+    bool good;
+    if (G == 1) good = decompress_g1<C>(pts + i * 2 * F, in + i * F, check_subgroup != 0);
+    else good = decompress_g2<C>(pts + i * 4 * F, in + i * 2 * F, check_subgroup != 0);
+    ok[i] = good ? 1 : 0;
 }
 
 // register-only IMAD.WIDE.U32 loop: the integer-pipe roofline denominator.  The multiplier operand is
@@ -985,6 +1007,78 @@ int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, c
     CU(cudaMemcpyAsync(out, dout, n * rec, cudaMemcpyDeviceToHost, sl.s->stream));
     CU(cudaStreamSynchronize(sl.s->stream));
     return BGLS_OK;
+}
+static int codec_dev(bgls_ctx* ctx, int curve, int group, bool compress, const void* d_in, size_t n, int check_subgroup,
+                     void* d_out, void* d_ok, cudaStream_t s) {
+    if (n == 0) return BGLS_OK;
+    const unsigned nb = (unsigned)((n + TB - 1) / TB);
+    const uint8_t* in = (const uint8_t*)d_in;
+    uint8_t *out = (uint8_t*)d_out, *ok = (uint8_t*)d_ok;
+    if (compress) {
+        if (curve == BGLS_ALTBN128) {
+            if (group == 1) k_compress<BN254, 1><<<nb, TB, 0, s>>>(in, n, out);
+            else k_compress<BN254, 2><<<nb, TB, 0, s>>>(in, n, out);
+        } else {
+            if (group == 1) k_compress<BLS381, 1><<<nb, TB, 0, s>>>(in, n, out);
+            else k_compress<BLS381, 2><<<nb, TB, 0, s>>>(in, n, out);
+        }
+    } else {
+        if (curve == BGLS_ALTBN128) {
+            if (group == 1) k_decompress<BN254, 1><<<nb, TB, 0, s>>>(in, n, check_subgroup, out, ok);
+            else k_decompress<BN254, 2><<<nb, TB, 0, s>>>(in, n, check_subgroup, out, ok);
+        } else {
+            if (group == 1) k_decompress<BLS381, 1><<<nb, TB, 0, s>>>(in, n, check_subgroup, out, ok);
+            else k_decompress<BLS381, 2><<<nb, TB, 0, s>>>(in, n, check_subgroup, out, ok);
+        }
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+int bgls_compress_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!pts || !out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    if (n == 0) return BGLS_OK;
+    SlotLock sl(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), bi = align_up(n * 2 * group * F), bo = align_up(n * group * F);
+    int rc = ensure_scratch(ctx, sl.s, bi + bo);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dout = din + bi;
+    CU(cudaMemcpyAsync(din, pts, n * 2 * group * F, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = codec_dev(ctx, curve, group, true, din, n, 0, dout, nullptr, sl.s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, dout, n * group * F, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
+    return BGLS_OK;
+}
+int bgls_decompress_points(bgls_ctx* ctx, int curve, int group, const uint8_t* in, size_t n, int check_subgroup,
+                           uint8_t* out_pts, uint8_t* out_ok) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!in || !out_pts || !out_ok))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    if (n == 0) return BGLS_OK;
+    SlotLock sl(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), bi = align_up(n * group * F), bo = align_up(n * 2 * group * F), bk = align_up(n);
+    int rc = ensure_scratch(ctx, sl.s, bi + bo + bk);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dout = din + bi, *dok = dout + bo;
+    CU(cudaMemcpyAsync(din, in, n * group * F, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = codec_dev(ctx, curve, group, false, din, n, check_subgroup, dout, dok, sl.s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_pts, dout, n * 2 * group * F, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaMemcpyAsync(out_ok, dok, n, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
+    return BGLS_OK;
+}
+int bgls_compress_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* stream) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!d_pts || !d_out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    return codec_dev(ctx, curve, group, true, d_pts, n, 0, d_out, nullptr, (cudaStream_t)stream);
+}
+int bgls_decompress_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_in, size_t n, int check_subgroup,
+                               void* d_out_pts, void* d_out_ok, void* stream) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (n && (!d_in || !d_out_pts || !d_out_ok))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    return codec_dev(ctx, curve, group, false, d_in, n, check_subgroup, d_out_pts, d_out_ok, (cudaStream_t)stream);
 }
 static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_off, size_t n, void* d_out, cudaStream_t s) {
     if (n == 0) return BGLS_OK;

@@ -67,8 +67,8 @@ class Point:
         return self._canon()
 
     def Marshal(self) -> bytes:
-        # compressed encodings are a wire-format row outside the hot path
-        raise NotImplementedError("compressed Marshal is out of scope for the accelerated path; use MarshalUncompressed")
+        """Compressed form, computed by the engine (curves/altbn128.go:81-89,203-221; bls12_381.go:57-59,118-120)."""
+        return self.curve._ctx().compress_points(self.curve.cid, self.group, self._canon(), 1)
 
     def Negate(self):
         """curves/altbn128.go:123-128,227-233; bls12_381.go:85-91,139-146."""
@@ -156,15 +156,25 @@ class CurveSystem:
             return None, False
         return Point(self, 2, b"".join(int(c).to_bytes(self.fp_bytes, "big") for c in coords)), True
 
-    def UnmarshalG1(self, data):
-        if data is None or len(data) != 2 * self.fp_bytes:
+    def _unmarshal(self, group, data):
+        """curves/altbn128.go:296-376, bls12_381.go:242-264: uncompressed or compressed by length; the compressed form
+        is decoded on the GPU (bls12-381 with the subgroup check the reference's Check() performs)."""
+        F = self.fp_bytes
+        if data is None:
             return None, False
-        return Point(self, 1, data), True
+        data = bytes(data)
+        if len(data) == 2 * group * F:
+            return Point(self, group, data), True
+        if len(data) != group * F:
+            return None, False
+        raw, ok = self._ctx().decompress_points(self.cid, group, data, 1, check_subgroup=(self.cid == BLS12_381))
+        return (Point(self, group, raw), True) if ok[0] else (None, False)
+
+    def UnmarshalG1(self, data):
+        return self._unmarshal(1, data)
 
     def UnmarshalG2(self, data):
-        if data is None or len(data) != 4 * self.fp_bytes:
-            return None, False
-        return Point(self, 2, data), True
+        return self._unmarshal(2, data)
 
     def UnmarshalGT(self, data):
         if data is None or len(data) != 12 * self.fp_bytes:

@@ -129,6 +129,24 @@ int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish);
 /* measured full-rate IMAD.WIDE.U32 throughput of this GPU (32x32+64 multiply-accumulates / s) */
 int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s);
 
+/* Point.Marshal (compressed form) -- curves/altbn128.go:81-89 (G1), :203-221 (G2); curves/bls12_381.go:57-59,118-120.
+ * pts: n uncompressed records; out: n compressed records of F (G1) / 2F (G2) bytes.
+ *   altbn128: x, bit 7 of byte 0 set iff 2y > q; G2 = x_im || x_re with one sign bit per y component.
+ *   bls12-381: the zcash serialisation of the upstream dis2/bls12 library (0x80 compressed, 0x40 infinity,
+ *   0x20 larger root) -- restated from the format's definition, the upstream source is not in the reference tree. */
+int bgls_compress_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out);
+int bgls_compress_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* stream);
+
+/* CurveSystem.UnmarshalG1 / UnmarshalG2 on compressed input -- curves/altbn128.go:296-376 (square roots
+ * curves/hash.go:178-223); curves/bls12_381.go:242-264.  out_pts: n uncompressed records (zeros where rejected);
+ * out_ok[i] = 1 when record i decoded to a curve point (or infinity), 0 when the reference would return
+ * (nil, false): malformed flags, coordinate >= q, or x not on the curve.  check_subgroup != 0 additionally
+ * requires r*P = infinity (the reference's bls12 path calls Check(); its altbn128 path does not). */
+int bgls_decompress_points(bgls_ctx* ctx, int curve, int group, const uint8_t* in, size_t n, int check_subgroup,
+                           uint8_t* out_pts, uint8_t* out_ok);
+int bgls_decompress_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_in, size_t n, int check_subgroup,
+                               void* d_out_pts, void* d_out_ok, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -358,6 +358,162 @@ class Curve:
             f[k] = (v[2 * idx + 1], v[2 * idx])
         return f
 
+
+    # ---- compressed wire formats -----------------------------------------------------
+    # altbn128: the reference's own codec (curves/altbn128.go:81-89, 203-221, 296-376).
+    #   G1: x (32 B, big-endian), bit 7 of byte 0 set iff 2y > q.          infinity = zeros
+    #   G2: x_im || x_re (64 B), bit 7 of x_im[0] iff 2 y_im > q, bit 7 of x_re[0] iff 2 y_re > q.
+    # bls12-381: the reference hands (un)marshalling to dis2/bls12 (curves/bls12_381.go:57-63,118-124,242-264), which is
+    # not in /root/reference; restated here as the zcash bls12-381 serialisation that library implements
+    # [upstream, from memory -- PARITY UNPINNED for this curve]:
+    #   G1: x (48 B); byte 0: 0x80 = compressed, 0x40 = infinity, 0x20 = y is the lexicographically larger root.
+    #   G2: x_c1 || x_c0 (96 B), same flags; "larger" compares (y_c1, y_c0).
+    def sqrt_fp2(self, a):
+        """calcComplexQuadRes (curves/hash.go:196-223), Adj & Rodriguez-Henriquez complex method; a = (re, im).
+        Returns some square root when a is a square, an arbitrary value otherwise (callers check)."""
+        p = self.p
+        re, im = a[0] % p, a[1] % p
+        if im == 0:
+            # the reference only handles a.re being a residue here; the other real case is i*sqrt(-re)
+            if self.is_quad_res(re):
+                return (self.sqrt_fp(re), 0)
+            return (0, self.sqrt_fp((-re) % p))
+        lam = self.sqrt_fp((re * re + im * im) % p)
+        inv2 = pow(2, -1, p)
+        delta = (re + lam) * inv2 % p
+        if not self.is_quad_res(delta):
+            delta = (re - lam) * inv2 % p
+        x0 = self.sqrt_fp(delta)
+        if x0 == 0:
+            return (0, 0)
+        x1 = pow(x0, -1, p) * inv2 % p * im % p
+        return (x0, x1)
+
+    def compress_g1(self, P):
+        n = self.nbytes
+        if self.name == "altbn128":
+            if P is None:
+                return bytes(n)
+            out = bytearray(self._be(P[0]))
+            if 2 * P[1] > self.p:
+                out[0] |= 0x80
+            return bytes(out)
+        if P is None:
+            return bytes([0xC0]) + bytes(n - 1)
+        out = bytearray(self._be(P[0]))
+        out[0] |= 0x80 | (0x20 if P[1] > (self.p - 1) // 2 else 0)
+        return bytes(out)
+
+    def compress_g2(self, Q):
+        n = self.nbytes
+        if self.name == "altbn128":
+            if Q is None:
+                return bytes(2 * n)
+            (xr, xi), (yr, yi) = Q
+            a, b = bytearray(self._be(xi)), bytearray(self._be(xr))
+            if 2 * yi > self.p:
+                a[0] |= 0x80
+            if 2 * yr > self.p:
+                b[0] |= 0x80
+            return bytes(a + b)
+        if Q is None:
+            return bytes([0xC0]) + bytes(2 * n - 1)
+        (x0, x1), (y0, y1) = Q
+        out = bytearray(self._be(x1) + self._be(x0))
+        half = (self.p - 1) // 2
+        larger = y1 > half if y1 != 0 else y0 > half
+        out[0] |= 0x80 | (0x20 if larger else 0)
+        return bytes(out)
+
+    def decompress_g1(self, data):
+        """-> (point or None for infinity, ok).  ok is False when x is not the abscissa of a curve point
+        (the reference's MakeG1Point(.., true) / upstream Unmarshal rejects it) or the encoding is malformed."""
+        n, p = self.nbytes, self.p
+        if len(data) != n:
+            return None, False
+        d = bytearray(data)
+        if self.name == "altbn128":
+            sgn = d[0] >= 128
+            d[0] &= 0x7F
+            x = int.from_bytes(d, "big")
+            if x == 0:
+                return None, True
+            if x >= p:
+                return None, False
+            y2 = self.x_to_y2(x)
+            y = self.sqrt_fp(y2)
+            if y * y % p != y2:
+                return None, False
+            if sgn != (2 * y > p):
+                y = (p - y) % p
+            return (x, y), True
+        if not d[0] & 0x80:
+            return None, False
+        inf, larger = bool(d[0] & 0x40), bool(d[0] & 0x20)
+        d[0] &= 0x1F
+        x = int.from_bytes(d, "big")
+        if inf:
+            return None, (x == 0 and not larger)
+        if x >= p:
+            return None, False
+        y2 = self.x_to_y2(x)
+        y = self.sqrt_fp(y2)
+        if y * y % p != y2:
+            return None, False
+        if larger != (y > (p - 1) // 2):
+            y = (p - y) % p
+        return (x, y), True
+
+    def decompress_g2(self, data):
+        n, p, F = self.nbytes, self.p, self.F2
+        if len(data) != 2 * n:
+            return None, False
+        d = bytearray(data)
+        if self.name == "altbn128":
+            si, sr = d[0] >= 128, d[n] >= 128
+            d[0] &= 0x7F
+            d[n] &= 0x7F
+            xi, xr = int.from_bytes(d[:n], "big"), int.from_bytes(d[n:], "big")
+            if xi == 0 and xr == 0:
+                return None, True
+            if xi >= p or xr >= p:
+                return None, False
+            x = (xr, xi)
+            y2 = F.add(F.mul(x, F.mul(x, x)), self.b2)
+            yr, yi = self.sqrt_fp2(y2)
+            # the reference fixes the two components independently (curves/altbn128.go:355-370)
+            if si != (2 * yi > p):
+                yi = (p - yi) % p
+            if sr != (2 * yr > p):
+                yr = (p - yr) % p
+            Q = (x, (yr, yi))
+            return (Q, True) if self.g2_on_curve(Q) else (None, False)
+        if not d[0] & 0x80:
+            return None, False
+        inf, larger = bool(d[0] & 0x40), bool(d[0] & 0x20)
+        d[0] &= 0x1F
+        x1, x0 = int.from_bytes(d[:n], "big"), int.from_bytes(d[n:], "big")
+        if inf:
+            return None, (x0 == 0 and x1 == 0 and not larger)
+        if x0 >= p or x1 >= p:
+            return None, False
+        x = (x0, x1)
+        y2 = F.add(F.mul(x, F.mul(x, x)), self.b2)
+        y = self.sqrt_fp2(y2)
+        if F.mul(y, y) != (y2[0] % p, y2[1] % p):
+            return None, False
+        half = (p - 1) // 2
+        is_larger = y[1] > half if y[1] != 0 else y[0] > half
+        if larger != is_larger:
+            y = ((p - y[0]) % p, (p - y[1]) % p)
+        return (x, y), True
+
+    def in_subgroup_g1(self, P):
+        return P is None or self.g1_mul(P, self.r) is None
+
+    def in_subgroup_g2(self, Q):
+        return Q is None or self.g2_mul(Q, self.r) is None
+
     # ---- hash to G1 ------------------------------------------------------------------
     def sqrt_fp(self, a):
         """calcQuadRes, curves/hash.go:178-190 (q = 3 mod 4 only)."""

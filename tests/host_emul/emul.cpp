@@ -210,3 +210,14 @@ extern "C" void emu_hash_to_g1(int curve, const uint8_t* msg, size_t len, uint8_
     if (curve == 0) hash_to_g1_keccak_ti<BN254>(out, msg, len);
     else hash_to_g1_ft<BLS381>(out, msg, len);
 }
+
+// ============================================================ compressed wire formats (host emulation of codec.cuh)
+#include "../../bgls_b200/csrc/codec.cuh"
+extern "C" void emu_compress(int curve, int group, const uint8_t* rec, uint8_t* out) {
+    if (curve == 0) { if (group == 1) compress_g1<BN254>(out, rec); else compress_g2<BN254>(out, rec); }
+    else { if (group == 1) compress_g1<BLS381>(out, rec); else compress_g2<BLS381>(out, rec); }
+}
+extern "C" int emu_decompress(int curve, int group, const uint8_t* in, int check_subgroup, uint8_t* rec) {
+    if (curve == 0) return group == 1 ? decompress_g1<BN254>(rec, in, check_subgroup) : decompress_g2<BN254>(rec, in, check_subgroup);
+    return group == 1 ? decompress_g1<BLS381>(rec, in, check_subgroup) : decompress_g2<BLS381>(rec, in, check_subgroup);
+}

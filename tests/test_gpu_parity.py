@@ -289,3 +289,47 @@ def test_concurrent_calls_from_host_threads(ctx, cid, c):
     for t in ths:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_compressed_wire_formats(ctx, cid, c):
+    """Point.Marshal / UnmarshalG1 / UnmarshalG2 on compressed input (curves/altbn128.go:81-89,203-221,296-376;
+    bls12_381.go:242-264) on the GPU: golden vectors, oracle parity on random and invalid records, ragged batch."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "compressed_golden.json")))[c.name]
+    nb = c.nbytes
+    for group, key in ((1, "g1"), (2, "g2")):
+        unc = b"".join(bytes.fromhex(e["uncompressed"]) for e in gold[key])
+        cmp_ = b"".join(bytes.fromhex(e["compressed"]) for e in gold[key])
+        n = len(gold[key])
+        assert ctx.compress_points(cid, group, unc, n) == cmp_
+        pts, ok = ctx.decompress_points(cid, group, cmp_, n, check_subgroup=True)
+        assert pts == unc and all(ok)
+    rng = random.Random(404 + cid)
+    flag = 0x80 if cid == 1 else 0
+    for group in (1, 2):
+        recs, want_pts, want_ok = [], [], []
+        dec = c.decompress_g1 if group == 1 else c.decompress_g2
+        marshal = c.marshal_g1 if group == 1 else c.marshal_g2
+        for i in range(75):   # random abscissas: about half are not on the curve
+            d = bytearray(rng.randrange(c.p).to_bytes(nb, "big") if group == 1 else
+                          rng.randrange(c.p).to_bytes(nb, "big") + rng.randrange(c.p).to_bytes(nb, "big"))
+            d[0] |= flag | (0x20 if (cid == 1 and i & 1) else 0) | (0x80 if (cid == 0 and i & 1 and d[0] < 0x30) else 0)
+            pt, ok = dec(bytes(d))
+            recs.append(bytes(d))
+            want_ok.append(ok)
+            want_pts.append(marshal(pt) if ok else bytes(2 * group * nb))
+        pts, ok = ctx.decompress_points(cid, group, b"".join(recs), len(recs))
+        assert ok == want_ok and pts == b"".join(want_pts)
+        assert 10 < sum(ok) < 65
+    # the curve mirror: Marshal / Unmarshal round trip, wrong length rejected (curves/curve_test.go:23-87)
+    from bgls_b200.curves import Altbn128, Bls12
+    curve = Altbn128 if cid == 0 else Bls12
+    for gen, un in ((curve.GetG1(), curve.UnmarshalG1), (curve.GetG2(), curve.UnmarshalG2)):
+        p = gen.Mul(rng.randrange(1, c.r))
+        q, ok = un(p.Marshal())
+        assert ok and q.Equals(p) and len(p.Marshal()) * 2 == len(p.MarshalUncompressed())
+        q, ok = un(p.MarshalUncompressed())
+        assert ok and q.Equals(p)
+        assert un(p.Marshal()[:-1]) == (None, False)

@@ -160,3 +160,59 @@ def test_hash_to_g1_reference_vectors(E, cid, c):
     for ln in (0, 1, 31, 32, 123, 124, 127, 128, 135, 136, 137, 200, 300):
         m = bytes(rng.randrange(256) for _ in range(ln))
         assert H(m) == c.marshal_g1(c.hash_to_g1(m)), ln
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_compressed_wire_formats(E, cid, c):
+    """codec.cuh on the host against the oracle restatement of curves/altbn128.go:81-89,203-221,296-376 (altbn128)
+    and of the zcash format the upstream bls12 library implements: round trips, both sign choices, infinity,
+    non-residue abscissas, unreduced coordinates, malformed flags, subgroup check."""
+    E.emu_compress.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p]
+    E.emu_decompress.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p]
+    nb = c.nbytes
+    rng = random.Random(31 + cid)
+
+    def comp(group, rec):
+        out = ctypes.create_string_buffer(group * nb)
+        E.emu_compress(cid, group, rec, out)
+        return out.raw
+
+    def decomp(group, data, sub=0):
+        out = ctypes.create_string_buffer(2 * group * nb)
+        ok = E.emu_decompress(cid, group, data, sub, out)
+        return out.raw, bool(ok)
+    for _ in range(6):
+        P = c.g1_mul(c.g1, rng.randrange(1, c.r))
+        Q = c.g2_mul(c.g2, rng.randrange(1, c.r))
+        for pt in (P, c.g1_neg(P)):
+            assert comp(1, c.marshal_g1(pt)) == c.compress_g1(pt)
+            assert decomp(1, c.compress_g1(pt), 1) == (c.marshal_g1(pt), True)
+        for pt in (Q, c.g2_neg(Q)):
+            assert comp(2, c.marshal_g2(pt)) == c.compress_g2(pt)
+            assert decomp(2, c.compress_g2(pt)) == (c.marshal_g2(pt), True)
+    assert decomp(2, c.compress_g2(c.g2), 1) == (c.marshal_g2(c.g2), True)
+    assert comp(1, c.marshal_g1(None)) == c.compress_g1(None) and decomp(1, c.compress_g1(None)) == (bytes(2 * nb), True)
+    assert comp(2, c.marshal_g2(None)) == c.compress_g2(None) and decomp(2, c.compress_g2(None)) == (bytes(4 * nb), True)
+    flag = 0x80 if cid == 1 else 0
+    seen = {True: 0, False: 0}
+    for x in list(range(1, 30)) + [c.p - 1, c.p, c.p + 1]:
+        for group in (1, 2):
+            d = bytearray(bytes((group - 1) * nb) + (x % (1 << (8 * nb - 3))).to_bytes(nb, "big"))
+            d[0] |= flag
+            want_pt, want_ok = (c.decompress_g1 if group == 1 else c.decompress_g2)(bytes(d))
+            rec, ok = decomp(group, bytes(d))
+            assert ok == want_ok, (group, x)
+            marshal = c.marshal_g1 if group == 1 else c.marshal_g2
+            assert rec == (marshal(want_pt) if want_ok else bytes(2 * group * nb))
+            seen[ok] += 1
+            if ok and group == 1 and cid == 1:
+                # bls12-381 G1 has a large cofactor: a random curve point is not in the subgroup
+                assert decomp(1, bytes(d), 1)[1] == c.in_subgroup_g1(want_pt)
+    assert seen[True] > 5 and seen[False] > 5
+    if cid == 1:   # malformed flags: not marked compressed; infinity with a non-zero body
+        d = bytearray(c.compress_g1(c.g1))
+        d[0] &= 0x7F
+        assert decomp(1, bytes(d)) == (bytes(2 * nb), False)
+        d = bytearray(c.compress_g1(None))
+        d[-1] = 1
+        assert decomp(1, bytes(d)) == (bytes(2 * nb), False)
