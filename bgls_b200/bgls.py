@@ -8,7 +8,9 @@ argument order and accept/reject behaviour follow the reference line by line:
     VerifyAggregateSignature        bgls/bgls.go:82-84   -> verifyAggSig bgls/bgls.go:94-119
     verifyMultiSignature            bgls/bgls.go:89-92
     AggregateSignatures / Keys      bgls/bgls.go:123-131
-    KoskSign / KoskVerify*          bgls/blsKosk.go:74-120
+    KoskSign / KoskVerify*          bgls/blsKosk.go:74-150 (incl. batch multi-signature and multiplicity)
+    DistinctMsg*                    bgls/blsDistinctMessage.go:22-57
+    VerifyAggregateSignatures       engine extension: many independent aggregate verifies in one batched launch
 
 The only computation done here is control flow; every pairing, point sum, scalar multiplication and
 hash-to-G1 goes through the CurveSystem (i.e. the CUDA engine).  `hash` parameters mirror the
@@ -62,8 +64,9 @@ def verifyAggSig(curve: CurveSystem, aggsig: Point, keys, msgs, allowDuplicates:
         return False
     if not allowDuplicates and containsDuplicateMessage(msgs):
         return False
-    hash = hash or curve.HashToG1
-    pts1 = [hash(m) for m in msgs] + [aggsig.Mul(-1)]
+    # the reference hashes in n goroutines (bgls.go:106-111); the default hash is one kernel launch for all messages
+    hashed = curve.HashToG1Many(msgs) if hash is None else [hash(m) for m in msgs]
+    pts1 = hashed + [aggsig.Mul(-1)]
     pts2 = list(keys) + [curve.GetG2()]
     aggPt, ok = curve.PairingProduct(pts1, pts2)
     if ok:
@@ -104,3 +107,59 @@ def KoskVerifyAggregateSignature(curve, aggsig, keys, msgs, hash=None):
 
 def KoskVerifyMultiSignature(curve, aggsig, keys, msg, hash=None):
     return verifyMultiSignature(curve, aggsig, keys, b"\x01" + bytes(msg), hash)
+
+
+def KoskVerifyBatchMultiSignature(curve, aggsigs, pubkeys, msgs):
+    """bgls/blsKosk.go:126-133: one aggregate check over the per-message aggregated keys."""
+    aggsig = AggregateSignatures(aggsigs)
+    keys = [AggregateKeys(pk) for pk in pubkeys]
+    return KoskVerifyAggregateSignature(curve, aggsig, keys, msgs)
+
+
+def KoskVerifyMultiSignatureWithMultiplicity(curve, aggsig, keys, multiplicity, msg):
+    """bgls/blsKosk.go:137-150: keys scaled by their multiplicities (ScalePoints), then the multi-signature check."""
+    from .curves import ScalePoints
+    if multiplicity is None:
+        return KoskVerifyMultiSignature(curve, aggsig, keys, msg)
+    if len(keys) != len(multiplicity):
+        return False
+    return KoskVerifyMultiSignature(curve, aggsig, ScalePoints(keys, [int(m) for m in multiplicity]), msg)
+
+
+# ---- Distinct messages (bgls/blsDistinctMessage.go): the public key is prepended to the message
+def DistinctMsgSign(curve, sk, m, hash=None):
+    msg = LoadPublicKey(curve, sk).MarshalUncompressed() + bytes(m)
+    return SignCustHash(sk, msg, hash or curve.HashToG1)
+
+
+def DistinctMsgVerifySingleSignature(curve, sig, pubkey, m):
+    return VerifySingleSignature(curve, sig, pubkey, pubkey.MarshalUncompressed() + bytes(m))
+
+
+def DistinctMsgVerifyAggregateSignature(curve, aggsig, keys, msgs):
+    if len(keys) != len(msgs):
+        return False
+    return verifyAggSig(curve, aggsig, keys, [k.MarshalUncompressed() + bytes(m) for k, m in zip(keys, msgs)], True)
+
+
+def VerifyAggregateSignatures(curve, items):
+    """Engine extension (BASELINE config 5, throughput mode): `items` = [(aggsig, keys, msgs), ...]; every entry gets
+    the verdict VerifyAggregateSignature would give it, with all hashes in one launch and all pairing products in
+    one batched launch."""
+    verdicts, todo, flat = [None] * len(items), [], []
+    for i, (aggsig, keys, msgs) in enumerate(items):
+        if len(keys) != len(msgs) or containsDuplicateMessage(msgs):
+            verdicts[i] = False
+        else:
+            todo.append(i)
+            flat += list(msgs)
+    hashed = curve.HashToG1Many(flat)
+    products, pos = [], 0
+    for i in todo:
+        aggsig, keys, msgs = items[i]
+        products.append((hashed[pos:pos + len(msgs)] + [aggsig.Mul(-1)], list(keys) + [curve.GetG2()]))
+        pos += len(msgs)
+    res = curve.PairingChecks(products)
+    for j, i in enumerate(todo):
+        verdicts[i] = bool(res[j]) if res is not None else False
+    return verdicts

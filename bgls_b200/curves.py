@@ -215,6 +215,30 @@ class CurveSystem:
         out = self._ctx().hash_to_g1(self.cid, [bytes(message)])
         return Point(self, 1, out)
 
+    def HashToG1Many(self, messages):
+        """The n concurrentHash goroutines of verifyAggSig (bgls/bgls.go:106-111,134-137) as ONE kernel launch."""
+        msgs = [bytes(m) for m in messages]
+        if not msgs:
+            return []
+        out = self._ctx().hash_to_g1(self.cid, msgs)
+        rec = 2 * self.fp_bytes
+        return [Point(self, 1, out[i * rec:(i + 1) * rec]) for i in range(len(msgs))]
+
+    def PairingChecks(self, products):
+        """Engine extension for throughput mode (BASELINE config 5): `products` is a list of (pts1, pts2) pairs of
+        equal-length Point lists; returns [prod_i e(pts1[i], pts2[i]) == 1] for each, all in one batched launch
+        (bgls_pairing_check_batch).  None when a product is malformed (the reference's (nil, false))."""
+        g1, g2, offs = [], [], [0]
+        for pts1, pts2 in products:
+            if len(pts1) != len(pts2) or any(not self._is(a, 1) for a in pts1) or any(not self._is(b, 2) for b in pts2):
+                return None
+            g1 += [p._canon() for p in pts1]
+            g2 += [p._canon() for p in pts2]
+            offs.append(offs[-1] + len(pts1))
+        if not products:
+            return []
+        return self._ctx().pairing_check_batch(self.cid, b"".join(g1), b"".join(g2), offs)
+
     # ---- the accelerated boundary
     def Pair(self, p1, p2):
         """curves/altbn128.go:130-141; bls12_381.go:228-236: (PointT, ok), ok False on a type mismatch."""

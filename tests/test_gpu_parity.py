@@ -247,6 +247,27 @@ def test_scheme_layer_end_to_end():
         msig = bgls.AggregateSignatures([bgls.KoskSign(curve, k[0], m) for k in ks])
         assert bgls.KoskVerifyMultiSignature(curve, msig, [k[1] for k in ks], m)
         assert not bgls.KoskVerifyMultiSignature(curve, msig, [k[1] for k in ks[:-1]], m)
+        # batch multi-signature (bgls/blsKosk.go:126-133), multiplicity (:137-150), distinct messages
+        ms = [bytes(rng.randrange(256) for _ in range(16)) for _ in range(3)]
+        groups = [[bgls.KeyGen(curve, rng) for _ in range(3)] for _ in ms]
+        msigs = [bgls.AggregateSignatures([bgls.KoskSign(curve, k[0], mm) for k in g]) for g, mm in zip(groups, ms)]
+        assert bgls.KoskVerifyBatchMultiSignature(curve, msigs, [[k[1] for k in g] for g in groups], ms)
+        assert not bgls.KoskVerifyBatchMultiSignature(curve, msigs, [[k[1] for k in g] for g in groups], ms[::-1])
+        mult = [1, 3, 2, 1, 1, 5, 1, 2]
+        msig_m = bgls.AggregateSignatures([bgls.KoskSign(curve, k[0], m).Mul(f) for k, f in zip(ks, mult)])
+        assert bgls.KoskVerifyMultiSignatureWithMultiplicity(curve, msig_m, [k[1] for k in ks], mult, m)
+        assert not bgls.KoskVerifyMultiSignatureWithMultiplicity(curve, msig, [k[1] for k in ks], mult, m)
+        assert not bgls.KoskVerifyMultiSignatureWithMultiplicity(curve, msig_m, [k[1] for k in ks], mult[:-1], m)
+        dsigs = [bgls.DistinctMsgSign(curve, k[0], mm) for k, mm in zip(keys, msgs)]
+        assert bgls.DistinctMsgVerifySingleSignature(curve, dsigs[0], pubs[0], msgs[0])
+        dagg = bgls.AggregateSignatures(dsigs)
+        assert bgls.DistinctMsgVerifyAggregateSignature(curve, dagg, pubs, msgs)
+        assert not bgls.DistinctMsgVerifyAggregateSignature(curve, dagg, pubs, msgs[::-1])
+        # many independent aggregate verifies in one batched launch: same verdicts as one call each
+        items = [(agg, pubs, msgs), (agg2, pubs, msgs), (agg, pubs[:N - 1], msgs), (agg, pubs, [msgs[1], msgs[0]] + msgs[2:]),
+                 (agg2, pubs + [vkf], msgs + [msgs[0]]), (dagg, pubs, msgs)]
+        assert bgls.VerifyAggregateSignatures(curve, items) == [bgls.VerifyAggregateSignature(curve, *it) for it in items]
+        assert bgls.VerifyAggregateSignatures(curve, items)[:2] == [True, False]
         # TestMul / TestAggregation of the curves package on the mirror (curves/curve_test.go:120-186)
         k = rng.randrange(curve.GetG1Order())
         inf, ok = curve.GetG1().Mul(k).Add(curve.GetG1().Mul(-k))
