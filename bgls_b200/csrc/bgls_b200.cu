@@ -592,7 +592,10 @@ size_t launch_miller(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const
         // one pairing per warp; the block size spreads the pairs over all SMs (small products) up to 16 warps per SM
         using P = typename PFile<M>::type;
         size_t wpb = (n + ctx->sms - 1) / ctx->sms;
-        if (wpb > (size_t)MP_MAXW) wpb = MP_MAXW;
+        // large products: two resident blocks per SM (shared memory: tables + one pooled slot file per warp;
+        // registers: 81 / 98 per thread) give more warps per sub-partition than one block of 16
+        const size_t big_wpb = P::L <= 10 ? 12 : 10;
+        if (wpb > big_wpb) wpb = big_wpb;
         const size_t nb = (n + wpb - 1) / wpb;
         k_mach_miller32<P><<<(unsigned)nb, (unsigned)wpb * 32, mach_smem_bytes<P>((int)wpb), s>>>(d.p, d.miller_p, P::MILLER_LEN, d.mulacc_p, fuse ? 1 : 0,
                                                                                              d_g1, d_g2, n, vals);

@@ -836,7 +836,8 @@ def build_miller_p(gen: Gen):
     D = cfg.twist == "D"
     A_ = cfg.xi_a
     gen.begin("MILLER")
-    raw = {n: gen.g("RAW." + n) for n in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")}
+    with gen.pool("QTMP", "RAW"):   # the raw inputs are dead after the first phase
+        raw = {n: gen.g("RAW." + n) for n in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")}
     for sl in raw.values():
         gen.set_ub(sl, p - 1)
     xP, yP = gen.g("xP"), gen.g("yP")
@@ -857,10 +858,11 @@ def build_miller_p(gen: Gen):
     lin += [gen.lin(FA[k][c], (gen.ONE if (k == 0 and c == 0) else gen.ZERO, 1)) for k in range(6) for c in range(2)]
     gen.lin_rounds(lin)
 
-    def lslots(name):
-        return {k: gen.g("%s.%s" % (name, k)) for k in ("x", "y", "tx", "ty")}
-    lines = {"y": lslots("LY"), "x": lslots("LX"), "c": lslots("LC")}
     pos = {"y": 0, "x": 1, "c": 3} if D else {"c": 0, "x": 2, "y": 3}
+
+    def lslots(name, ps):
+        return {k: gen.g("%s.%s" % (name, k)) for k in (("x", "y", "tx", "ty") if ps > 0 else ("x", "y"))}
+    lines = {"y": lslots("LY", pos["y"]), "x": lslots("LX", pos["x"]), "c": lslots("LC", pos["c"])}
     linemap = {pos[k]: lines[k] for k in ("y", "x", "c")}
 
     def m2(dst, u, v):       # Fp2 product
@@ -893,12 +895,16 @@ def build_miller_p(gen: Gen):
         return tasks
 
     # ---- f^2 by complex squaring over Fp6 = Fp2[v]/(v^3 - xi), v = w^2 (see Gen._f12_sqr), in three stages
-    S = [gen.fp2("SQ.S%d" % j) for j in range(3)]
-    Bq = [gen.fp2("SQ.B%d" % j) for j in range(3)]
-    d1 = {j: {"tx": gen.g("SQ.d1_%d.tx" % j), "ty": gen.g("SQ.d1_%d.ty" % j)} for j in (1, 2)}
-    dB = {j: {"tx": gen.g("SQ.dB_%d.tx" % j), "ty": gen.g("SQ.dB_%d.ty" % j)} for j in (1, 2)}
-    Tt = [gen.fp2("SQ.T%d" % j) for j in range(3)]
-    Ss = [gen.fp2("SQ.P%d" % j) for j in range(3)]
+    # The temporaries of the squaring (live from phase B to phase D of a doubling), of the addition step (live only
+    # between two doublings) and of the product-tree multiplication (after the loop) are never live together: they
+    # share physical slots (pool "PTMP"), which keeps the per-warp slot file small enough for three blocks per SM.
+    with gen.pool("PTMP", "SQR"):
+        S = [gen.fp2("SQ.S%d" % j) for j in range(3)]
+        Bq = [gen.fp2("SQ.B%d" % j) for j in range(3)]
+        d1 = {j: {"tx": gen.g("SQ.d1_%d.tx" % j), "ty": gen.g("SQ.d1_%d.ty" % j)} for j in (1, 2)}
+        dB = {j: {"tx": gen.g("SQ.dB_%d.tx" % j), "ty": gen.g("SQ.dB_%d.ty" % j)} for j in (1, 2)}
+        Tt = [gen.fp2("SQ.T%d" % j) for j in range(3)]
+        Ss = [gen.fp2("SQ.P%d" % j) for j in range(3)]
 
     def sqr_lin_a(a):
         c0, c1 = [a[0], a[2], a[4]], [a[1], a[3], a[5]]
@@ -949,10 +955,12 @@ def build_miller_p(gen: Gen):
         return t
 
     # ---- doubling: homogeneous projective, E = 3b'Z^2 = BB8 * BE8
-    XY, Bd, X2, YZ, E = gen.fp2("XY"), gen.fp2("B"), gen.fp2("X2"), gen.fp2("YZ"), gen.fp2("E")
-    BmF, BpF = gen.fp2("BmF"), gen.fp2("BpF")
-    X3, Sd, EE, Z3, BB, BE = gen.fp2("X3"), gen.fp2("S"), gen.fp2("EE"), gen.fp2("Z3"), gen.fp2("BB"), gen.fp2("BE")
-    LYp, LXp = gen.fp2("LYp"), gen.fp2("LXp")
+    # doubling temporaries are dead during an addition step and vice versa: second pool "QTMP"
+    E, LYp, LXp = gen.fp2("E"), gen.fp2("LYp"), gen.fp2("LXp")   # used by both steps
+    with gen.pool("QTMP", "DBL"):
+        XY, Bd, X2, YZ = gen.fp2("XY"), gen.fp2("B"), gen.fp2("X2"), gen.fp2("YZ")
+        BmF, BpF = gen.fp2("BmF"), gen.fp2("BpF")
+        X3, Sd, EE, Z3, BB, BE = gen.fp2("X3"), gen.fp2("S"), gen.fp2("EE"), gen.fp2("Z3"), gen.fp2("BB"), gen.fp2("BE")
 
     def dbl_dot1():
         return m2(XY, X, Y) + m2(Bd, Y, Y) + m2(X2, X, X) + m2(YZ, Y, Z) + m2(E, BB8, BE8)
@@ -977,10 +985,14 @@ def build_miller_p(gen: Gen):
         return t
 
     # ---- mixed addition T += Q' = (Qx, Qy) with its line, four DOT + four LIN stages
-    yqZ, xqZ, TH, LA = gen.fp2("yqZ"), gen.fp2("xqZ"), gen.fp2("TH"), gen.fp2("LA")
-    Cc, Dd, LCp = gen.fp2("Cc"), gen.fp2("Dd"), gen.fp2("LCp")
-    Ee, Ff, Gg, H, GmH = gen.fp2("Ee"), gen.fp2("Ff"), gen.fp2("Gg"), gen.fp2("H"), gen.fp2("GmH")
-    AX3, ATt, EY, AZ3, EE2 = gen.fp2("AX3"), gen.fp2("ATt"), gen.fp2("EY"), gen.fp2("AZ3"), gen.fp2("EE2")
+    with gen.pool("QTMP", "ADD"):      # 12 Fp2 = as many slots as the doubling temporaries
+        yqZ, xqZ, TH, LA = gen.fp2("yqZ"), gen.fp2("xqZ"), gen.fp2("TH"), gen.fp2("LA")
+        Cc, Dd, LCp = gen.fp2("Cc"), gen.fp2("Dd"), gen.fp2("LCp")
+        Ee, Ff, Gg, H, GmH = gen.fp2("Ee"), gen.fp2("Ff"), gen.fp2("Gg"), gen.fp2("H"), gen.fp2("GmH")
+    with gen.pool("PTMP", "ADD"):      # the rest next to the squaring temporaries (dead between two doublings)
+        AX3, ATt, EY, AZ3, EE2 = gen.fp2("AX3"), gen.fp2("ATt"), gen.fp2("EY"), gen.fp2("AZ3"), gen.fp2("EE2")
+        if D:
+            Q1x, Q1y, Q2x, Q2y, nQ2y = gen.fp2("Q1x"), gen.fp2("Q1y"), gen.fp2("Q2x"), gen.fp2("Q2y"), gen.fp2("nQ2y")
 
     def add_dot1(Qx, Qy):
         return m2(yqZ, Qy, Z) + m2(xqZ, Qx, Z) + m2(E, BB8, BE8)
@@ -1061,7 +1073,6 @@ def build_miller_p(gen: Gen):
         g1 = f2pow(xi, (p - 1) // 6, p)
         g2c = gen.const2("G2", f2pow(g1, 2, p))
         g3c = gen.const2("G3", f2pow(g1, 3, p))
-        Q1x, Q1y, Q2x, Q2y, nQ2y = gen.fp2("Q1x"), gen.fp2("Q1y"), gen.fp2("Q2x"), gen.fp2("Q2y"), gen.fp2("nQ2y")
 
         def frobq(dx, dy, sx, sy):
             # conj(s) * g = (s.x g.x + s.y g.y) + (s.x g.y - s.y g.x) i
@@ -1099,13 +1110,16 @@ def build_mulacc_p(gen: Gen, FA):
     """Program MULACC of the signed 32-lane file: FA <- FA * GB in place (product trees).  Every dot of 12 terms is
     computed as two half dots on two lanes (temporaries), then one LIN phase sums the halves into FA."""
     p, A_ = gen.cfg.p, gen.cfg.xi_a
-    GB = gen.f12("GB")
+    with gen.pool("PTMP", "MUL"):
+        GB = gen.f12("GB")
     gen.begin("MULACC")
     for k in range(6):
         for c in range(2):
             gen.set_ub(FA[k][c], TREE_P * p)
             gen.set_ub(GB[k][c], TREE_P * p)
-    dv = {j: {"tx": gen.g("MUL.d%d.tx" % j), "ty": gen.g("MUL.d%d.ty" % j)} for j in range(1, 6)}   # xi * GB_j (j = 0 never wraps)
+    with gen.pool("PTMP", "MUL"):
+        dv = {j: {"tx": gen.g("MUL.d%d.tx" % j), "ty": gen.g("MUL.d%d.ty" % j)} for j in range(1, 6)}   # xi * GB_j (j = 0 never wraps)
+        mul_tmp = {(k, c, h): gen.g("MUL.%s%d_%d" % (h, k, c)) for k in range(6) for c in range(2) for h in ("lo", "hi")}
     lin = []
     for j in range(1, 6):
         lin += [gen.lin(dv[j]["tx"], (GB[j][0], A_), (GB[j][1], -1)), gen.lin(dv[j]["ty"], (GB[j][0], 1), (GB[j][1], A_))]
@@ -1122,7 +1136,7 @@ def build_mulacc_p(gen: Gen, FA):
                 re.append([(FA[i][0], dv[j]["tx"]), (FA[i][1], dv[j]["ty"], -1)])
                 im.append([(FA[i][0], dv[j]["ty"]), (FA[i][1], dv[j]["tx"])])
         for c, parts in ((0, re), (1, im)):
-            lo, hi = gen.g("MUL.lo%d_%d" % (k, c)), gen.g("MUL.hi%d_%d" % (k, c))
+            lo, hi = mul_tmp[(k, c, "lo")], mul_tmp[(k, c, "hi")]
             halves += [(lo, sum(parts[:3], [])), (hi, sum(parts[3:], []))]
             comb.append(gen.lin(FA[k][c], (lo, 1), (hi, 1)))
     gen.dot(halves)
