@@ -268,16 +268,48 @@ __global__ void __launch_bounds__(TB) k_scale(const uint8_t* __restrict__ pts, c
     jac_store<C>(out + i * rec, r);
 }
 
-// hash-to-G1, one message per thread (messages concatenated, offsets[n+1])
+// hash-to-G1 (messages concatenated, offsets[n+1]); both kernels spread one message over several lanes because the
+// per-message work is a chain of ~570-multiplication exponentiations:
+//   altbn128  -- 8 lanes per message try 8 consecutive counters of the try-and-increment loop at once, the lowest
+//                successful counter wins (what the sequential loop of hash.go:53-77 would have found first)
+//   bls12-381 -- 2 lanes per message, one per half (G1_0 / G1_1) of the Fouque-Tibouchi hash, summed by the even lane
 template <class C>
-__global__ void __launch_bounds__(TB) k_hash_to_g1(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
-                                                   uint8_t* __restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t* m = msgs + off[i];
-    const size_t len = (size_t)(off[i + 1] - off[i]);
-    if constexpr (C::IS_BN) hash_to_g1_keccak_ti<C>(out + i * 2 * C::FP_BYTES, m, len);
-    else hash_to_g1_ft<C>(out + i * 2 * C::FP_BYTES, m, len);
+__global__ void __launch_bounds__(TB) k_hash_to_g1_bn(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
+                                                      uint8_t* __restrict__ out) {
+    constexpr int LPM = 8;
+    const size_t i = ((size_t)blockIdx.x * TB + threadIdx.x) / LPM;
+    const int sub = threadIdx.x % LPM, grp = (threadIdx.x & 31) / LPM;
+    const bool active = i < n;
+    const uint8_t* m = active ? msgs + off[i] : msgs;
+    const size_t len = active ? (size_t)(off[i + 1] - off[i]) : 0;
+    bool done = !active;
+    for (int round = 0; round < 256 / LPM; round++) {
+        Fp<C> px, root;
+        const bool ok = !done && bn_hash_try<C>(px, root, (uint8_t)(round * LPM + sub), m, len);
+        const unsigned hits = (__ballot_sync(0xFFFFFFFFu, ok) >> (grp * LPM)) & ((1u << LPM) - 1);
+        if (!done && hits) {
+            if (sub == __ffs(hits) - 1) bn_hash_finish<C>(out + i * 2 * C::FP_BYTES, px, root, m, len);
+            done = true;
+        }
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+    }
+}
+template <class C>
+__global__ void __launch_bounds__(TB) k_hash_to_g1_bls(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
+                                                       uint8_t* __restrict__ out) {
+    __shared__ Jac<Fp<C>> sh[TB / 2];
+    const size_t i = ((size_t)blockIdx.x * TB + threadIdx.x) / 2;
+    const int half = threadIdx.x & 1;
+    Jac<Fp<C>> P;
+    P.inf = true;
+    if (i < n) ft_half<C>(P, msgs + off[i], (size_t)(off[i + 1] - off[i]), half);
+    if (half) sh[threadIdx.x / 2] = P;
+    __syncwarp();
+    if (!half && i < n) {
+        Jac<Fp<C>> S;
+        jac_add(S, P, sh[threadIdx.x / 2]);
+        jac_store<C>(out + i * 2 * C::FP_BYTES, S);
+    }
 }
 
 // compressed wire formats, one point per thread (codec.cuh)
@@ -1085,9 +1117,10 @@ int bgls_decompress_points_dev(bgls_ctx* ctx, int curve, int group, const void* 
 }
 static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_off, size_t n, void* d_out, cudaStream_t s) {
     if (n == 0) return BGLS_OK;
-    const unsigned nb = (unsigned)((n + TB - 1) / TB);
-    if (curve == BGLS_ALTBN128) k_hash_to_g1<BN254><<<nb, TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
-    else k_hash_to_g1<BLS381><<<nb, TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    if (curve == BGLS_ALTBN128)
+        k_hash_to_g1_bn<BN254><<<(unsigned)((n * 8 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    else
+        k_hash_to_g1_bls<BLS381><<<(unsigned)((n * 2 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
     ctx->launches++;
     CU(cudaGetLastError());
     return BGLS_OK;

@@ -180,23 +180,33 @@ template <class C> HD void fp_from_digest32(Fp<C>& r, const uint8_t* d) {
 }
 
 // ---------------------------------------------------------------- altbn128: tryAndIncrementEvm (hash.go:53-77)
+// one try: keccak(counter || msg) mod q is the abscissa of a curve point?  (px, root) valid when true
+template <class C> HD bool bn_hash_try(Fp<C>& px, Fp<C>& root, uint8_t counter, const uint8_t* msg, size_t len) {
+    uint8_t h[32];
+    keccak256_prefixed(h, counter, msg, len);
+    Fp<C> y2, chk;
+    fp_from_digest32<C>(px, h);  // h mod q
+    g1_x_to_y2(y2, px);
+    fp_sqrt_candidate(root, y2);
+    fp_sqr(chk, root);
+    return fp_eq(chk, y2);
+}
+// the sign of y comes from keccak(255 || msg) (hash.go:68-72)
+template <class C> HD void bn_hash_finish(uint8_t* out, const Fp<C>& px, Fp<C>& root, const uint8_t* msg, size_t len) {
+    uint8_t h[32];
+    keccak256_prefixed(h, 255, msg, len);
+    if (h[31] & 1) fp_neg(root, root);
+    g1_store_affine<C>(out, px, root);
+}
 template <class C> HDNI void hash_to_g1_keccak_ti(uint8_t* out, const uint8_t* msg, size_t len) {
     uint8_t counter = 0;
     while (true) {
-        uint8_t h[32];
-        keccak256_prefixed(h, counter, msg, len);
-        counter++;
-        Fp<C> px, y2, root, chk;
-        fp_from_digest32<C>(px, h);  // h mod q
-        g1_x_to_y2(y2, px);
-        fp_sqrt_candidate(root, y2);
-        fp_sqr(chk, root);
-        if (fp_eq(chk, y2)) {
-            keccak256_prefixed(h, 255, msg, len);
-            if (h[31] & 1) fp_neg(root, root);
-            g1_store_affine<C>(out, px, root);
+        Fp<C> px, root;
+        if (bn_hash_try<C>(px, root, counter, msg, len)) {
+            bn_hash_finish<C>(out, px, root, msg, len);
             return;
         }
+        counter++;
     }
 }
 
@@ -237,23 +247,28 @@ template <class C> HD void sw_encode(Fp<C>& x, Fp<C>& y, const Fp<C>& t) {
     fp_sub(x0, z, tmp);     // x0 = z - t w
     fp_neg(x1, x0);
     fp_sub(x1, x1, one);    // x1 = -1 - x0
+    // the candidates are tested in the reference's order (hash.go:120-160); the residue test and the square root
+    // share one exponentiation: r = v^((q+1)/4) is a root iff r^2 == v (0 counts as a residue, hash.go:254-265)
+    Fp<C> chk;
+    x = x0;
     g1_x_to_y2(y2, x0);
-    if (fp_is_quad_res(y2)) {
-        x = x0;
-    } else {
+    fp_sqrt_candidate(y, y2);
+    fp_sqr(chk, y);
+    if (!fp_eq(chk, y2)) {
+        x = x1;
         g1_x_to_y2(y2, x1);
-        if (fp_is_quad_res(y2)) {
-            x = x1;
-        } else {
+        fp_sqrt_candidate(y, y2);
+        fp_sqr(chk, y);
+        if (!fp_eq(chk, y2)) {
             fp_mul(tmp, A, inv);    // 1/B
             fp_mul(tmp, A, tmp);    // A/B = 1/w
             fp_sqr(tmp, tmp);
             fp_add(x2, tmp, one);   // x2 = 1 + 1/w^2
             x = x2;
             g1_x_to_y2(y2, x2);
+            fp_sqrt_candidate(y, y2);
         }
     }
-    fp_sqrt_candidate(y, y2);
     if (fp_parity(y) != fp_parity(t)) fp_neg(y, y);
 }
 template <class C> HD void ft_point(Jac<Fp<C>>& P, const uint8_t* digest64) {
@@ -277,13 +292,17 @@ template <class C> HD void ft_point(Jac<Fp<C>>& P, const uint8_t* digest64) {
                              0x8c, 0x00, 0xaa, 0xab, 0x00, 0x00, 0xaa, 0xab};
     jac_mul(P, Q, cof);
 }
-template <class C> HDNI void hash_to_g1_ft(uint8_t* out, const uint8_t* msg, size_t len) {
+// one of the two independent halves of hashToG1BlindingAbstracted (bls12_381.go:362-376): blake2b(msg || tag) -> t ->
+// Shallue-van de Woestijne point -> times the cofactor
+template <class C> HDNI void ft_half(Jac<Fp<C>>& P, const uint8_t* msg, size_t len, int which) {
     uint8_t d[64];
+    blake2b512_tagged(d, msg, len, which ? "G1_1" : "G1_0");
+    ft_point<C>(P, d);
+}
+template <class C> HDNI void hash_to_g1_ft(uint8_t* out, const uint8_t* msg, size_t len) {
     Jac<Fp<C>> P1, P2, S;
-    blake2b512_tagged(d, msg, len, "G1_0");
-    ft_point<C>(P1, d);
-    blake2b512_tagged(d, msg, len, "G1_1");
-    ft_point<C>(P2, d);
+    ft_half<C>(P1, msg, len, 0);
+    ft_half<C>(P2, msg, len, 1);
     jac_add(S, P1, P2);
     jac_store<C>(out, S);
 }
