@@ -558,6 +558,8 @@ class Gen:
           (z3', z2') from (z4, z5): z3' = 3(z4^2 + xi z5^2) - 2 z3,  z2' = 6 z4 (xi z5) + 2 z2
         tower view: c0 = (a0, a2, a4), c1 = (a1, a3, a5); z0=c0.0 z4=c0.1 z3=c0.2 z2=c1.0 z1=c1.1 z5=c1.2"""
         assert d is not a
+        if self.signed:
+            return self._f12_cycsqr_signed(d, a)
         z = {0: a[0], 4: a[2], 3: a[4], 2: a[1], 1: a[3], 5: a[5]}
         zd = {0: d[0], 4: d[2], 3: d[4], 2: d[1], 1: d[3], 5: d[5]}
         A = self.cfg.xi_a
@@ -581,6 +583,38 @@ class Gen:
                      (zd[o][1], [(ux, c6y), (uy, c6x), (z[o][1], C2)])]
         self.lin_rounds(lin)
         self.dot(dots)
+
+    def _f12_cycsqr_signed(self, d, a):
+        """The same squaring on a signed slot file: ONE DOT phase of the 18 products of at most two terms
+             p1 = ux^2 - uy^2, p2 = ux uy, p3 = vx^2 - vy^2, p4 = vx vy, p5 = ux vx - uy vy, p6 = ux vy + uy vx
+        per (u, v) pair plus the 12 scalings q_e = -2 z_e, q_o = 2 z_o (products with constants, so that the bounds
+        contract: a LIN term -2 z would grow the bound by 2.5x per squaring), then ONE LIN phase
+             z_e' = 3 (u^2 + xi v^2) - 2 z_e = (3 p1 + 3A p3 - 6 p4 + q_e.x,  6 p2 + 3 p3 + 6A p4 + q_e.y)
+             z_o' = 6 [xi] u v + 2 z_o
+        (no scaled operand copies, no split dots: two phases per squaring instead of three)."""
+        z = {0: a[0], 4: a[2], 3: a[4], 2: a[1], 1: a[3], 5: a[5]}
+        zd = {0: d[0], 4: d[2], 3: d[4], 2: d[1], 1: d[3], 5: d[5]}
+        A = self.cfg.xi_a
+        dots, lin, ps = [], [], {}
+        C2, CN2 = self.const("C2", 2), self.const("CN2", -2)
+        groups = ((0, 1, 0, 1, False), (2, 3, 4, 5, False), (4, 5, 3, 2, True))
+        for n, (u, v, e, o, twist_cross) in enumerate(groups):
+            (ux, uy), (vx, vy) = z[u], z[v]
+            ps[n] = tuple(self.g("CYS.%d.p%d" % (n, k)) for k in range(1, 7)) + tuple(self.g("CYS.%d.q%d" % (n, k)) for k in range(4))
+            p1, p2, p3, p4, p5, p6, qex, qey, qox, qoy = ps[n]
+            dots += [(p1, [(ux, ux), (uy, uy, -1)]), (p2, [(ux, uy)]), (p3, [(vx, vx), (vy, vy, -1)]), (p4, [(vx, vy)]),
+                     (p5, [(ux, vx), (uy, vy, -1)]), (p6, [(ux, vy), (uy, vx)]),
+                     (qex, [(z[e][0], CN2)]), (qey, [(z[e][1], CN2)]), (qox, [(z[o][0], C2)]), (qoy, [(z[o][1], C2)])]
+        self.dot(dots)
+        for n, (u, v, e, o, twist_cross) in enumerate(groups):
+            p1, p2, p3, p4, p5, p6, qex, qey, qox, qoy = ps[n]
+            lin += [self.lin(zd[e][0], (p1, 3), (p3, 3 * A), (p4, -6), (qex, 1)),
+                    self.lin(zd[e][1], (p2, 6), (p3, 3), (p4, 6 * A), (qey, 1))]
+            if not twist_cross:
+                lin += [self.lin(zd[o][0], (p5, 6), (qox, 1)), self.lin(zd[o][1], (p6, 6), (qoy, 1))]
+            else:
+                lin += [self.lin(zd[o][0], (p5, 6 * A), (p6, -6), (qox, 1)), self.lin(zd[o][1], (p5, 6), (p6, 6 * A), (qoy, 1))]
+        self.lin_rounds(lin)
 
     def declare(self, slots, bound):
         """Loop invariant: assume `bound` for these slots from here on (checked with check_le)."""
@@ -1373,7 +1407,7 @@ class Sim:
 def build_all(cfg):
     """Three independent slot files: "M" (16-lane MILLER, MUL_AB, MUL_BA), "F" (FINALEXP) and "P" (32-lane
     pipelined MILLER with signed terms: the latency path)."""
-    gm, gf = Gen(cfg), Gen(cfg, lanes=32, tm=6, split=True)
+    gm, gf = Gen(cfg), Gen(cfg, lanes=32, tm=6, split=True, signed=True)
     gp = Gen(cfg, lanes=32, tm=6, signed=True)
     io = {}
     io["p_miller_in"], io["P_FA"] = build_miller_p(gp)
