@@ -13,7 +13,7 @@
 namespace bgls {
 
 constexpr int MWPB = 4;                 // warps per block
-constexpr int MP_MAXW = 16;             // k_mach_miller32: pairings (warps) per block, at most
+constexpr int MP_MAXW = 12;             // k_mach_miller32 / k_mach_tree32: pairings (warps) per block, at most
 constexpr int MFIN_THREADS = 256;       // k_mach_finish: one working warp, the others only stage the tables
 constexpr int MGPB = MWPB * 2;          // groups per block
 
@@ -139,8 +139,11 @@ __device__ __forceinline__ void mach_block_tree(uint32_t* gbase, const MachTable
     }
 }
 
+// launch bounds: for the 10-limb curve 12 warps per block and two blocks per SM keep the kernel at 80 registers (81
+// without them: the allocation granule then makes a 12-warp block take more than half of the register file); the
+// 14-limb curve needs 98 registers and is left alone (forcing 80 spills: measured 16 % slower)
 template <class P>
-__global__ void __launch_bounds__(512) k_mach_miller32(MachTables tb, const uint16_t* __restrict__ prog, int plen,
+__global__ void __launch_bounds__(MP_MAXW * 32, P::L <= 10 ? 2 : 1) k_mach_miller32(MachTables tb, const uint16_t* __restrict__ prog, int plen,
                                                       const uint16_t* __restrict__ prog_mul, int fuse,
                                                       const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                       size_t n, uint32_t* __restrict__ vals) {
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(512) k_mach_miller32(MachTables tb, const uint
 // ---------------------------------------------------------------- K2p
 // One level of the product tree: every block multiplies up to blockDim.x / 32 values (machine form) into one.
 template <class P>
-__global__ void __launch_bounds__(512) k_mach_tree32(MachTables tb, const uint16_t* __restrict__ prog_mul,
+__global__ void __launch_bounds__(MP_MAXW * 32, P::L <= 10 ? 2 : 1) k_mach_tree32(MachTables tb, const uint16_t* __restrict__ prog_mul,
                                                     const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
     extern __shared__ uint32_t sm[];
     constexpr int L = P::L;
