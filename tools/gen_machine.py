@@ -268,7 +268,7 @@ class Gen:
             for dst in new_ub:
                 new_ub[dst] += phase.K * cfg.p
                 assert new_ub[dst] < cfg.R
-        sig = (phase.kind, tuple((d, tuple(t)) for d, t in phase.tasks))
+        sig = (phase.kind, tuple((d, tuple(t)) for d, t in phase.tasks), getattr(phase, "nplain", None))
         if sig in self.cache:
             pid = self.cache[sig]   # bounds of every execution are re-verified by verify_program()
             if getattr(phase, "K", 0) > getattr(self.phases[pid], "K", 0):
@@ -366,6 +366,41 @@ class Gen:
         self.emit(ph)
         if comb:
             self.lin_rounds([self.lin(dst, (a, 1), (b, 1)) for dst, a, b in comb])
+
+    def kdot(self, triples, plain):
+        """DOT phase in Karatsuba-lane form.  `triples`: [(re_dst, im_dst, [(a, b), ...])] with a, b Fp2 slot pairs: the
+        Fp2 sum of products sum_t a_t * b_t is computed by THREE lanes,  Q = sum a.y b.y,  P = sum a.x b.x,
+        S = sum (a.x + a.y)(b.x + b.y)  (operand sums formed on the fly, at most tm/2 terms), which the interpreter
+        combines by warp shuffle into re = P - Q and im = S - P - Q before the reduction.  `plain`: ordinary DOT
+        tasks of at most tm/2 terms on the remaining lanes.  For bounds, hazards and the exact simulator the phase is
+        the equivalent schoolbook DOT phase; the lane form only exists in the emitted tables."""
+        assert self.signed and 3 * len(triples) + len(plain) <= self.lanes
+        cfg = self.cfg
+        half = self.tm // 2
+        assert self.kdot_fits(), "K-lane columns would overflow"
+        for _, _, terms in triples:
+            for a, b in terms:
+                for sl in (a[0], a[1], b[0], b[1]):   # small top limbs: see kdot_fits
+                    assert (self.ub[sl] >> (cfg.W * (cfg.L - 1))) < (1 << 15), "operand too large for the K-lane column bound"
+        ph = Phase("DOT")
+        ph.triples, ph.nplain = [], len(plain)
+        for dst, terms in plain:
+            assert len(terms) <= half
+        ph.tasks = list(plain)
+        for re, im, terms in triples:
+            assert 0 < len(terms) <= half
+            ph.triples.append((re, im, [(a, b) for a, b in terms]))
+            ph.tasks += [(re, sum(([(a[0], b[0]), (a[1], b[1], -1)] for a, b in terms), [])),
+                         (im, sum(([(a[0], b[1]), (a[1], b[0])] for a, b in terms), []))]
+        self.emit(ph)
+
+    def kdot_fits(self):
+        """Signed 64-bit columns of a K-lane phase: operand sums have W+1 bits.  The fullest column is index L-2 with
+        L-1 products of two full limbs per term (column L-1 has L products, but two of them involve a top limb, which
+        is below 2^15 for every operand: checked per operand in kdot); the reduction adds L products of W-bit limbs."""
+        cfg, half = self.cfg, self.tm // 2
+        worst = half * ((cfg.L - 1) * (1 << (2 * cfg.W + 2)) + 2 * (1 << (cfg.W + 1 + 16))) + cfg.L * (1 << (2 * cfg.W)) + (1 << 40)
+        return self.signed and worst < (1 << 63)
 
     # ---- LIN helpers (return task tuples)
     def kfor(self, slot):
@@ -869,6 +904,9 @@ def build_miller_p(gen: Gen):
     assert gen.signed and gen.lanes == 32
     D = cfg.twist == "D"
     A_ = cfg.xi_a
+    # Karatsuba-lane form of the two big DOT phases (3 terms instead of 6): the operand sums have 29 bits, which the
+    # signed 64-bit columns only hold for the 10-limb curve
+    KD = gen.kdot_fits()
     gen.begin("MILLER")
     with gen.pool("QTMP", "RAW"):   # the raw inputs are dead after the first phase
         raw = {n: gen.g("RAW." + n) for n in ("xP", "yP", "xQ.x", "xQ.y", "yQ.x", "yQ.y")}
@@ -911,6 +949,16 @@ def build_miller_p(gen: Gen):
         out = [gen.lin(l["x"], *x_terms), gen.lin(l["y"], *y_terms)]
         if ps > 0:   # positions that wrap around w^6 = xi need xi * coefficient
             out += [gen.lin(l["tx"], *(mul(x_terms, A_) + neg(y_terms))), gen.lin(l["ty"], *(x_terms + mul(y_terms, A_)))]
+        return out
+
+    def sparse_triples(d, a):
+        out = []
+        for k in range(6):
+            terms = []
+            for ps, l in sorted(linemap.items()):
+                i = (k - ps) % 6
+                terms.append((a[i], (l["x"], l["y"]) if k - ps >= 0 else (l["tx"], l["ty"])))
+            out.append((d[k][0], d[k][1], terms))
         return out
 
     def sparse_tasks(d, a):
@@ -976,6 +1024,27 @@ def build_miller_p(gen: Gen):
         c0, c1 = [a[0], a[2], a[4]], [a[1], a[3], a[5]]
         return fp6_dots(Tt, c0, c1, d1) + fp6_dots(Ss, S, Bq, dB)
 
+    def fp6_triples(dst, u, v, dv):
+        out = []
+        for k in range(3):
+            terms = []
+            for i in range(3):
+                j = (k - i) % 3
+                terms.append((u[i], v[j] if i <= k else (dv[j]["tx"], dv[j]["ty"])))
+            out.append((dst[k][0], dst[k][1], terms))
+        return out
+
+    def sqr_triples(a):
+        c0, c1 = [a[0], a[2], a[4]], [a[1], a[3], a[5]]
+        return fp6_triples(Tt, c0, c1, d1) + fp6_triples(Ss, S, Bq, dB)
+
+    def big_dot(triples, schoolbook, plain):
+        """One of the two wide DOT phases of an iteration: Karatsuba lanes when the curve allows it."""
+        if KD:
+            gen.kdot(triples, plain)
+        else:
+            gen.dot(schoolbook + plain)
+
     def sqr_lin_b(d):
         nc0, nc1 = [d[0], d[2], d[4]], [d[1], d[3], d[5]]
         t = [gen.lin(nc0[0][0], (Ss[0][0], 1), (Tt[0][0], -1), (Tt[2][0], -A_), (Tt[2][1], 1)),
@@ -994,7 +1063,7 @@ def build_miller_p(gen: Gen):
     with gen.pool("QTMP", "DBL"):
         XY, Bd, X2, YZ = gen.fp2("XY"), gen.fp2("B"), gen.fp2("X2"), gen.fp2("YZ")
         BmF, BpF = gen.fp2("BmF"), gen.fp2("BpF")
-        X3, Sd, EE, Z3, BB, BE = gen.fp2("X3"), gen.fp2("S"), gen.fp2("EE"), gen.fp2("Z3"), gen.fp2("BB"), gen.fp2("BE")
+        X3, EE, Z3, BB, BE = gen.fp2("X3"), gen.fp2("EE"), gen.fp2("Z3"), gen.fp2("BB"), gen.fp2("BE")
 
     def dbl_dot1():
         return m2(XY, X, Y) + m2(Bd, Y, Y) + m2(X2, X, X) + m2(YZ, Y, Z) + m2(E, BB8, BE8)
@@ -1005,13 +1074,16 @@ def build_miller_p(gen: Gen):
         return t + line_tasks(lines["c"], pos["c"], [(Bd[0], 1), (E[0], -1)], [(Bd[1], 1), (E[1], -1)])
 
     def dbl_dot2():
-        return (m2(X3, XY, BmF) + m2(Sd, BpF, BpF) + m2(EE, E, E) + m2(Z3, Bd, YZ) + m2(BB, Bd, Bd) + m2(BE, Bd, E) +
+        # (B + 3E)^2 = B^2 + 6 B E + 9 E^2 is a combination of BB, BE, EE: no product of its own (14 tasks, so that the
+        # 18 Karatsuba lanes of the squaring fit beside them)
+        return (m2(X3, XY, BmF) + m2(EE, E, E) + m2(Z3, Bd, YZ) + m2(BB, Bd, Bd) + m2(BE, Bd, E) +
                 m2fp(LYp, YZ, yP) + m2fp(LXp, X2, xP))
 
     def dbl_lin2():
-        # (4X3, 4Y3, 4Z3) = (2 XY (B-F), (B+F)^2 - 12 E^2, 8 B YZ);  ly = 2 YZ yP,  lx = -3 X^2 xP
+        # (4X3, 4Y3, 4Z3) = (2 XY (B-F), (B+F)^2 - 12 E^2, 8 B YZ), F = 3E: (B+F)^2 - 12 E^2 = BB + 6 BE - 3 EE;
+        # ly = 2 YZ yP,  lx = -3 X^2 xP
         t = [gen.lin(X[0], (X3[0], 2)), gen.lin(X[1], (X3[1], 2)),
-             gen.lin(Y[0], (Sd[0], 1), (EE[0], -12)), gen.lin(Y[1], (Sd[1], 1), (EE[1], -12)),
+             gen.lin(Y[0], (BB[0], 1), (BE[0], 6), (EE[0], -3)), gen.lin(Y[1], (BB[1], 1), (BE[1], 6), (EE[1], -3)),
              gen.lin(Z[0], (Z3[0], 8)), gen.lin(Z[1], (Z3[1], 8)),
              gen.lin(BB8[0], (BB[0], 8)), gen.lin(BB8[1], (BB[1], 8)), gen.lin(BE8[0], (BE[0], 8)), gen.lin(BE8[1], (BE[1], 8))]
         t += line_tasks(lines["y"], pos["y"], [(LYp[0], 2)], [(LYp[1], 2)])
@@ -1019,11 +1091,12 @@ def build_miller_p(gen: Gen):
         return t
 
     # ---- mixed addition T += Q' = (Qx, Qy) with its line, four DOT + four LIN stages
-    with gen.pool("QTMP", "ADD"):      # 12 Fp2 = as many slots as the doubling temporaries
+    with gen.pool("QTMP", "ADD"):      # 11 Fp2 = as many slots as the doubling temporaries
         yqZ, xqZ, TH, LA = gen.fp2("yqZ"), gen.fp2("xqZ"), gen.fp2("TH"), gen.fp2("LA")
         Cc, Dd, LCp = gen.fp2("Cc"), gen.fp2("Dd"), gen.fp2("LCp")
-        Ee, Ff, Gg, H, GmH = gen.fp2("Ee"), gen.fp2("Ff"), gen.fp2("Gg"), gen.fp2("H"), gen.fp2("GmH")
+        Ee, Ff, Gg, H = gen.fp2("Ee"), gen.fp2("Ff"), gen.fp2("Gg"), gen.fp2("H")
     with gen.pool("PTMP", "ADD"):      # the rest next to the squaring temporaries (dead between two doublings)
+        GmH = gen.fp2("GmH")
         AX3, ATt, EY, AZ3, EE2 = gen.fp2("AX3"), gen.fp2("ATt"), gen.fp2("EY"), gen.fp2("AZ3"), gen.fp2("EE2")
         if D:
             Q1x, Q1y, Q2x, Q2y, nQ2y = gen.fp2("Q1x"), gen.fp2("Q1y"), gen.fp2("Q2x"), gen.fp2("Q2y"), gen.fp2("nQ2y")
@@ -1070,11 +1143,11 @@ def build_miller_p(gen: Gen):
 
     def add_step(Qx, Qy, more):
         """FB = f^2, dbl line ready.  Ends with f in FA and (if `more`) the first DOT of the next doubling issued."""
-        gen.dot(sparse_tasks(FA, FB) + add_dot1(Qx, Qy))
+        big_dot(sparse_triples(FA, FB), sparse_tasks(FA, FB), add_dot1(Qx, Qy))
         lin1(add_lin1())
         gen.dot(add_dot2(Qx, Qy))
         lin1(add_lin2())
-        gen.dot(sparse_tasks(FB, FA) + add_dot3())
+        big_dot(sparse_triples(FB, FA), sparse_tasks(FB, FA), add_dot3())
         lin1(add_lin3() + [gen.lin(FA[k][c], (FB[k][c], 1)) for k in range(6) for c in range(2)])
         gen.dot(add_dot4())
         lin1(add_lin4())
@@ -1092,10 +1165,10 @@ def build_miller_p(gen: Gen):
         last = n_ == len(body) - 1
         more = (not last) or False
         lin1(sqr_lin_a(FA) + dbl_lin1())
-        gen.dot(sqr_dot(FA) + dbl_dot2())
+        big_dot(sqr_triples(FA), sqr_dot(FA), dbl_dot2())
         lin1(sqr_lin_b(FB) + dbl_lin2())
         if dgt == 0:
-            gen.dot(sparse_tasks(FA, FB) + (dbl_dot1() if more else []))
+            big_dot(sparse_triples(FA, FB), sparse_tasks(FA, FB), dbl_dot1() if more else [])
         elif dgt == 1:
             add_step(xQ, yQ, more)
         else:
@@ -1121,7 +1194,7 @@ def build_miller_p(gen: Gen):
             lin1(add_lin1())
             gen.dot(add_dot2(Qx, Qy))
             lin1(add_lin2())
-            gen.dot(sparse_tasks(dst, src) + add_dot3())
+            big_dot(sparse_triples(dst, src), sparse_tasks(dst, src), add_dot3())
             lin1(add_lin3())
             gen.dot(add_dot4())
             lin1(add_lin4())
@@ -1131,7 +1204,7 @@ def build_miller_p(gen: Gen):
         lin1(add_lin1())
         gen.dot(add_dot2(Q2x, nQ2y))
         lin1(add_lin2())
-        gen.dot(sparse_tasks(FA, FB))
+        big_dot(sparse_triples(FA, FB), sparse_tasks(FA, FB), [])
     else:
         gen.f12_conj(FA, FA)  # x < 0
     return raw, FA
@@ -1513,6 +1586,35 @@ def emit_tables(path):
             TM, REC = gen.tm, 2 * gen.tm + 2
             hdr, rec = [], []
             for ph in gen.phases:
+                if getattr(ph, "triples", None) is not None:
+                    # Karatsuba-lane DOT phase (kind 3): every term is (a1 + a2) * (b1 + b2); lanes 3j, 3j+1, 3j+2 hold
+                    # the Q, P, S parts of triple j (P writes re, S writes im), then the plain tasks;
+                    # record: [0] dst, [1 + 2t], [2 + 2t] = a1 (bit 15: minus), a2, [1 + TM + 2t], [2 + TM + 2t] = b1, b2
+                    Z = ref(gen.ZERO)
+                    ntr, half = len(ph.triples), TM // 2
+                    hdr.append(3 | (half << 8) | (ntr << 16) | (getattr(ph, "K", 0) << 24))
+                    lanes_ = []
+                    for re, im, terms in ph.triples:
+                        lanes_.append((0xFFFF, [(a[1], None, b[1], None) for a, b in terms]))            # Q
+                        lanes_.append((ref(re), [(a[0], None, b[0], None) for a, b in terms]))            # P
+                        lanes_.append((ref(im), [(a[0], a[1], b[0], b[1]) for a, b in terms]))            # S
+                    for dst, terms in ph.tasks[:ph.nplain]:
+                        lanes_.append((ref(dst), [(t[0], None, t[1], None, (t[2] if len(t) > 2 else 1)) for t in terms]))
+                    assert len(lanes_) <= gen.lanes
+                    for lane in range(gen.lanes):
+                        r = [0xFFFF] + [Z] * (2 * TM) + [0]
+                        if lane < len(lanes_):
+                            r[0] = lanes_[lane][0]
+                            for t, term in enumerate(lanes_[lane][1]):
+                                a1, a2, b1, b2 = term[:4]
+                                sgn = term[4] if len(term) > 4 else 1
+                                r[1 + 2 * t] = ref(a1) | (0x8000 if sgn < 0 else 0)
+                                r[2 + 2 * t] = ref(a2) if a2 is not None else Z
+                                r[1 + TM + 2 * t] = ref(b1)
+                                r[2 + TM + 2 * t] = ref(b2) if b2 is not None else Z
+                        assert len(r) == REC
+                        rec += r
+                    continue
                 hdr.append({"DOT": 0, "LIN": 1, "INV": 2}[ph.kind] | (ph.T << 8) | ((len(ph.tasks) & 0xFF) << 16) | (getattr(ph, "K", 0) << 24))
                 for lane in range(gen.lanes):
                     r = [0xFFFF] + [ref(gen.ZERO)] * (2 * TM) + [0]
