@@ -120,11 +120,12 @@ template <class M> HD void mach_dot(const MachView<M>& mv, const uint16_t* rec, 
 }
 
 // Karatsuba-lane DOT phase (kind 3, signed files): every term is (a1 + a2) * (b1 + b2) with the operand sums formed
-// on the fly (W+1 bits: the generator proves that the signed columns hold them).  Lanes 3j, 3j+1, 3j+2 accumulate the
-// Q = sum a.y b.y, P = sum a.x b.x, S = sum (a.x+a.y)(b.x+b.y) parts of one Fp2 sum of products; after the combination
-// (mach_kdot_combine on the device, by warp shuffle) the P lane reduces re = P - Q and the S lane im = S - P - Q.
+// on the fly (W+1 bits).  Lanes 3j, 3j+1, 3j+2 accumulate the Q = sum a.y b.y, P = sum a.x b.x,
+// S = sum (a.x+a.y)(b.x+b.y) parts of one Fp2 sum of products modulo 2^64 (unsigned: S may wrap, exactly); after the
+// combination (mach_kdot_combine on the device, by warp shuffle) the P lane reduces re = P - Q and the S lane
+// im = S - P - Q, which the generator proves to fit the signed range (Gen.kdot_fits).
 // record: [0] dst, [1 + 2t], [2 + 2t] = a1 (bit 15: minus), a2, [1 + TM + 2t], [2 + TM + 2t] = b1, b2
-template <class M> HD void mach_kdot_acc(const MachView<M>& mv, const uint16_t* rec, int T, long long* acc) {
+template <class M> HD void mach_kdot_acc(const MachView<M>& mv, const uint16_t* rec, int T, unsigned long long* acc) {
     constexpr int L = M::L;
 #pragma unroll
     for (int i = 0; i < 2 * L; i++) acc[i] = 0;
@@ -146,25 +147,29 @@ template <class M> HD void mach_kdot_acc(const MachView<M>& mv, const uint16_t* 
 #pragma unroll
         for (int i = 0; i < L; i++)
 #pragma unroll
-            for (int j = 0; j < L; j++) acc[i + j] += (long long)sa[i] * (long long)sb[j];
+            for (int j = 0; j < L; j++) acc[i + j] += (unsigned long long)((long long)sa[i] * (long long)sb[j]);
     }
 }
-template <class M> HD void mach_kdot_finish(uint32_t* out, long long* acc, uint32_t K) {
+template <class M> HD void mach_kdot_finish(uint32_t* out, const unsigned long long* uacc, uint32_t K) {
     constexpr int L = M::L;
+    long long acc[2 * L];
 #pragma unroll
-    for (int i = 0; i < L; i++) acc[L + i] += (long long)((unsigned long long)K * M::p(i));
+    for (int i = 0; i < L; i++) {
+        acc[i] = (long long)uacc[i];
+        acc[L + i] = (long long)(uacc[L + i] + (unsigned long long)K * M::p(i));
+    }
     mach_montred<M, long long>(out, acc);
 }
 #ifdef __CUDA_ARCH__
 // lanes (3j, 3j+1, 3j+2) = (Q, P, S) for j < ntr: P <- P - Q, S <- S - (P + Q); two shuffles per column
-template <class M> __device__ __forceinline__ void mach_kdot_combine(long long* acc, int ntr, int lane) {
+template <class M> __device__ __forceinline__ void mach_kdot_combine(unsigned long long* acc, int ntr, int lane) {
     const int role = lane < 3 * ntr ? lane % 3 : -1;
 #pragma unroll
     for (int c = 0; c < 2 * M::L; c++) {
-        const long long x = __shfl_up_sync(0xFFFFFFFFu, acc[c], 1);
-        long long sum = acc[c];
+        const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, acc[c], 1);
+        unsigned long long sum = acc[c];
         if (role == 1) { sum = acc[c] + x; acc[c] -= x; }
-        const long long y = __shfl_up_sync(0xFFFFFFFFu, sum, 1);
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, sum, 1);
         if (role == 2) acc[c] -= y;
     }
 }
@@ -389,7 +394,7 @@ template <class M> HD void mach_phase_lane(const MachView<M>& mv, const MachTabl
 #ifdef __CUDA_ARCH__
     if constexpr (M::SIGNED && M::LANES == 32) {
         if (kind == 3) {   // the whole warp is here: the phase kind is uniform
-            long long acc[2 * M::L];
+            unsigned long long acc[2 * M::L];
             mach_kdot_acc<M>(mv, rec, T, acc);
             mach_kdot_combine<M>(acc, (h >> 16) & 0xFF, lane);
             mach_kdot_finish<M>(out, acc, h >> 24);

@@ -100,13 +100,13 @@ template <class M, class T> struct HostMach {
             uint32_t outs[M::LANES][M::L];
             if constexpr (M::SIGNED) {
                 if ((h & 0xFF) == 3) {   // Karatsuba-lane DOT phase: accumulate per lane, combine the (Q, P, S) triples, reduce
-                    static long long acc[M::LANES][2 * M::L];
+                    static unsigned long long acc[M::LANES][2 * M::L];
                     for (int lane = 0; lane < M::LANES; lane++)
                         mach_kdot_acc<M>(mv, tb.rec + ((size_t)ph * M::LANES + lane) * M::REC, Tn, acc[lane]);
                     const int ntr = (h >> 16) & 0xFF;
                     for (int j = 0; j < ntr; j++)
                         for (int c = 0; c < 2 * M::L; c++) {
-                            const long long q = acc[3 * j][c], pp = acc[3 * j + 1][c];
+                            const unsigned long long q = acc[3 * j][c], pp = acc[3 * j + 1][c];
                             acc[3 * j + 1][c] = pp - q;
                             acc[3 * j + 2][c] -= pp + q;
                         }

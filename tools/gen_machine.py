@@ -378,10 +378,6 @@ class Gen:
         cfg = self.cfg
         half = self.tm // 2
         assert self.kdot_fits(), "K-lane columns would overflow"
-        for _, _, terms in triples:
-            for a, b in terms:
-                for sl in (a[0], a[1], b[0], b[1]):   # small top limbs: see kdot_fits
-                    assert (self.ub[sl] >> (cfg.W * (cfg.L - 1))) < (1 << 15), "operand too large for the K-lane column bound"
         ph = Phase("DOT")
         ph.triples, ph.nplain = [], len(plain)
         for dst, terms in plain:
@@ -395,11 +391,12 @@ class Gen:
         self.emit(ph)
 
     def kdot_fits(self):
-        """Signed 64-bit columns of a K-lane phase: operand sums have W+1 bits.  The fullest column is index L-2 with
-        L-1 products of two full limbs per term (column L-1 has L products, but two of them involve a top limb, which
-        is below 2^15 for every operand: checked per operand in kdot); the reduction adds L products of W-bit limbs."""
+        """64-bit columns of a K-lane phase.  The three partial sums are accumulated modulo 2^64 (unsigned, exact), so
+        S = sum (a.x+a.y)(b.x+b.y) may wrap; what has to fit the signed range is what the reduction sees after the
+        combination: |P - Q| and |S - P - Q| = |sum a.x b.y + a.y b.x|, at most tm/2 terms of 2 L products of W-bit
+        limbs, plus the L products the reduction adds per column and the offset K p."""
         cfg, half = self.cfg, self.tm // 2
-        worst = half * ((cfg.L - 1) * (1 << (2 * cfg.W + 2)) + 2 * (1 << (cfg.W + 1 + 16))) + cfg.L * (1 << (2 * cfg.W)) + (1 << 40)
+        worst = half * 2 * cfg.L * (1 << (2 * cfg.W)) + cfg.L * (1 << (2 * cfg.W)) + (1 << 40)
         return self.signed and worst < (1 << 63)
 
     # ---- LIN helpers (return task tuples)
