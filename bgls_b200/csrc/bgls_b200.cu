@@ -596,7 +596,7 @@ template <class M, class MT, class F, class FT, class P, class PT> int upload_ma
     CU(cudaFuncSetAttribute(k_mach_import<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<M>(MGPB)));
     CU(cudaFuncSetAttribute(k_mach_finish<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<F>(1)));
     CU(cudaFuncSetAttribute(k_mach_miller32<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<P>(MP_MAXW)));
-    CU(cudaFuncSetAttribute(k_mach_tree32<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<P>(MP_MAXW)));
+    CU(cudaFuncSetAttribute(k_mach_tree32<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mach_smem_bytes<P>(MT_MAXW)));
     return BGLS_OK;
 }
 
@@ -656,7 +656,7 @@ int mach_tree(bgls_ctx* ctx, const MachDev& d, uint32_t* buf0, uint32_t* buf1, s
     }
     while (cnt > 1 && !ctx->miller16) {   // binary in-block trees, 16 values per block and level
         using P = typename PFile<M>::type;
-        const size_t wpb = cnt < (size_t)MP_MAXW ? cnt : (size_t)MP_MAXW;
+        const size_t wpb = cnt < (size_t)MT_MAXW ? cnt : (size_t)MT_MAXW;
         const size_t nout = (cnt + wpb - 1) / wpb;
         k_mach_tree32<P><<<(unsigned)nout, (unsigned)wpb * 32, mach_smem_bytes<P>((int)wpb), s>>>(d.p, d.mulacc_p, cur, cnt, oth);
         ctx->launches++;

@@ -178,6 +178,29 @@ template <class M> __device__ __forceinline__ void mach_kdot_combine(unsigned lo
 template <class M> HD void mach_lin(const MachView<M>& mv, const uint16_t* rec, int T, uint32_t* out) {
     constexpr int L = M::L, W = M::W;
     constexpr uint32_t MASK = (1u << W) - 1;
+    if constexpr (M::SIGNED) {
+        // signed files: dst = Normalize(sum c_t * s_t + k p) with two's complement coefficients and ONE offset constant
+        // per task (record field 2 TM + 1), signed columns, arithmetic carries
+        long long acc[L];
+        uint32_t k[L];
+        mach_load<M>(k, mv, rec[2 * M::TM + 1]);
+#pragma unroll
+        for (int i = 0; i < L; i++) acc[i] = (long long)k[i];
+        for (int t = 0; t < T; t++) {
+            const int c = (int)(signed char)(rec[1 + M::TM + t] & 0xFFu);
+            uint32_t v[L];
+            mach_load<M>(v, mv, rec[1 + t]);
+#pragma unroll
+            for (int i = 0; i < L; i++) acc[i] += (long long)c * (long long)(int)v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < L - 1; i++) {
+            acc[i + 1] += acc[i] >> W;
+            out[i] = (uint32_t)acc[i] & MASK;
+        }
+        out[L - 1] = (uint32_t)acc[L - 1];
+        return;
+    }
     unsigned long long acc[L];
 #pragma unroll
     for (int i = 0; i < L; i++) acc[i] = 0;

@@ -13,7 +13,8 @@
 namespace bgls {
 
 constexpr int MWPB = 4;                 // warps per block
-constexpr int MP_MAXW = 12;             // k_mach_miller32 / k_mach_tree32: pairings (warps) per block, at most
+constexpr int MP_MAXW = 12;             // k_mach_miller32: pairings (warps) per block, at most
+constexpr int MT_MAXW = 16;             // k_mach_tree32: values (warps) per block, at most
 constexpr int MFIN_THREADS = 256;       // k_mach_finish: one working warp, the others only stage the tables
 constexpr int MGPB = MWPB * 2;          // groups per block
 
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(MP_MAXW * 32, P::L <= 10 ? 2 : 1) k_mach_mille
 // ---------------------------------------------------------------- K2p
 // One level of the product tree: every block multiplies up to blockDim.x / 32 values (machine form) into one.
 template <class P>
-__global__ void __launch_bounds__(MP_MAXW * 32, P::L <= 10 ? 2 : 1) k_mach_tree32(MachTables tb, const uint16_t* __restrict__ prog_mul,
+__global__ void __launch_bounds__(MT_MAXW * 32) k_mach_tree32(MachTables tb, const uint16_t* __restrict__ prog_mul,
                                                     const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
     extern __shared__ uint32_t sm[];
     constexpr int L = P::L;

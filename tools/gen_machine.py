@@ -138,6 +138,11 @@ class Gen:
         for K in KP_SET:
             if 2 * K * p >= cfg.R:
                 break
+            if signed:
+                # signed files never load the borrow-free K p vectors (one offset constant per LIN task instead):
+                # K stays a choice of the bound analysis only
+                self.KP[K] = ("kp", K)
+                continue
             idx = len(self.cvals)
             self.cslots["KP%d" % K] = idx
             self.cvals.append(cfg.kp_limbs(K))
@@ -189,6 +194,21 @@ class Gen:
         self.cints.append(v)
         self.ub[("c", idx)] = v
         return ("c", idx)
+
+    def offset_const(self, k):
+        """Constant slot holding the plain limbs of k * p (not reduced; never a DOT operand)."""
+        if k == 0:
+            return self.ZERO
+        name = "KT%d" % k
+        if name not in self.cslots:
+            v = k * self.cfg.p
+            assert v < self.cfg.R
+            idx = len(self.cvals)
+            self.cslots[name] = idx
+            self.cvals.append(self.cfg.limbs(v))
+            self.cints.append(v)
+            self.ub[("c", idx)] = None
+        return ("c", self.cslots[name])
 
     def const2(self, name, val2):
         return (self.const(name + ".x", val2[0]), self.const(name + ".y", val2[1]))
@@ -263,6 +283,13 @@ class Gen:
                         ub += -coef * K * cfg.p
             assert ub < cfg.R, ("value bound exceeds R", ub.bit_length())
             new_ub[dst] = ub
+        if phase.kind == "LIN" and self.signed:
+            # signed files: the interpreter accumulates sum c_t * s_t with signed c_t and adds ONE constant per task,
+            # (sum over the negative terms of |c_t| K_t) * p -- the same value as the term-wise K_t p - s_t form
+            phase.kt = []
+            for dst, terms in phase.tasks:
+                kt = sum(-coef * K for _, coef, K in terms if coef < 0)
+                phase.kt.append(self.offset_const(kt))
         if phase.kind == "DOT" and getattr(phase, "K", 0):
             assert phase.K < 256
             for dst in new_ub:
@@ -1629,6 +1656,11 @@ def emit_tables(path):
                                 assert r[1 + t] < 0x8000
                                 if len(term) > 2 and term[2] < 0:
                                     r[1 + t] |= 0x8000   # minus sign: the interpreter negates the first operand
+                            elif gen.signed:
+                                slot, coef, K = term
+                                r[1 + t] = ref(slot)
+                                assert abs(coef) < 128
+                                r[1 + TM + t] = coef & 0xFF      # two's complement coefficient
                             else:
                                 slot, coef, K = term
                                 r[1 + t] = ref(slot)
@@ -1636,6 +1668,8 @@ def emit_tables(path):
                                 kp = gen.KP[K][1] if coef < 0 else 0
                                 assert abs(coef) < 128 and kp < 256
                                 r[1 + TM + t] = abs(coef) | (0x80 if coef < 0 else 0) | (kp << 8)
+                        if ph.kind == "LIN" and gen.signed:
+                            r[2 * TM + 1] = ref(ph.kt[lane])   # the task's offset constant (k * p)
                     assert len(r) == REC
                     rec += r
             out.append("static const uint32_t %s_PHASE_HDR[%d] = {%s};" % (n, len(hdr), ", ".join(str(h) for h in hdr)))
