@@ -1645,6 +1645,8 @@ def emit_tables(path):
                     if ph.kind == "LIN":
                         for t in range(TM):
                             r[1 + TM + t] = 0
+                        if gen.signed:
+                            r[2 * TM + 1] = ref(gen.ZERO)   # idle lanes: a constant, never a slot another lane writes
                     if lane < len(ph.tasks):
                         dst, terms = ph.tasks[lane]
                         r[0] = ref(dst)
