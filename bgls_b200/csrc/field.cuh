@@ -133,18 +133,30 @@ template <class C> HD void fp_mul(Fp<C>& r, const Fp<C>& a, const Fp<C>& b) {
 }
 template <class C> HD void fp_sqr(Fp<C>& r, const Fp<C>& a) { fp_mul(r, a, a); }
 
-// a^e, e = nl 32-bit little-endian limbs (public exponent)
+// a^e, e = nl 32-bit little-endian limbs (public exponent: every thread takes the same branches).
+// Fixed 4-bit windows: 14 multiplications for the table, then 4 squarings and at most one multiplication per nibble
+// (the exponents here are (q-2), (q+1)/4, (q-1)/2: about a quarter fewer multiplications than bit by bit).
 template <class C> HDNI void fp_pow(Fp<C>& r, const Fp<C>& a, const uint32_t* e, int nl) {
-    Fp<C> acc, base = a;
-    fp_set(acc, C::R1());
+    Fp<C> tab[16];
+    fp_set(tab[0], C::R1());
+    tab[1] = a;
+    for (int k = 2; k < 16; k++) fp_mul(tab[k], tab[k - 1], a);
+    Fp<C> acc;
     bool started = false;
-    for (int i = nl * 32 - 1; i >= 0; i--) {
-        if (started) fp_sqr(acc, acc);
-        if ((e[i >> 5] >> (i & 31)) & 1) {
-            if (started) fp_mul(acc, acc, base);
-            else { acc = base; started = true; }
+    for (int i = nl * 8 - 1; i >= 0; i--) {
+        const uint32_t nib = (e[i >> 3] >> (4 * (i & 7))) & 0xFu;
+        if (started) {
+            fp_sqr(acc, acc);
+            fp_sqr(acc, acc);
+            fp_sqr(acc, acc);
+            fp_sqr(acc, acc);
+            if (nib) fp_mul(acc, acc, tab[nib]);
+        } else if (nib) {
+            acc = tab[nib];
+            started = true;
         }
     }
+    if (!started) fp_set(acc, C::R1());
     r = acc;
 }
 template <class C> HD void fp_inv(Fp<C>& r, const Fp<C>& a) { fp_pow(r, a, C::PM2(), C::N); }
