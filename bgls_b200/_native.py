@@ -20,6 +20,7 @@ EXPORTS = [
     "bgls_pairing_check_batch", "bgls_pairing_product_dev", "bgls_miller_product_dev", "bgls_final_exp_product_dev",
     "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_hash_to_g1", "bgls_hash_to_g1_dev", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
     "bgls_compress_points", "bgls_compress_points_dev", "bgls_decompress_points", "bgls_decompress_points_dev",
+    "bgls_verify_aggregate_signature",
 ]
 
 _lib = None
@@ -64,6 +65,7 @@ def load():
     L.bgls_compress_points_dev.argtypes = [vp, i, i, vp, sz, vp, vp]
     L.bgls_decompress_points.argtypes = [vp, i, i, cp, sz, i, cp, cp]
     L.bgls_decompress_points_dev.argtypes = [vp, i, i, vp, sz, i, vp, vp, vp]
+    L.bgls_verify_aggregate_signature.argtypes = [vp, i, cp, ctypes.POINTER(ctypes.c_uint64), sz, cp, cp, i, ip]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
     L.bgls_set_profiling.argtypes = [vp, i]
@@ -146,6 +148,25 @@ class Context:
         out = ctypes.create_string_buffer(max(1, n * 2 * group * FP_BYTES[curve]))
         self._chk(self._L.bgls_scale_points(self._h, curve, group, pts, scalars, n, out))
         return out.raw[: n * 2 * group * FP_BYTES[curve]]
+
+    def verify_aggregate_signature(self, curve, msgs, keys: bytes, sig: bytes, allow_duplicates: bool = False) -> bool:
+        """verifyAggSig (bgls/bgls.go:94-119) in one engine call: msgs is a list of bytes, keys the packed G2 records."""
+        n = len(msgs)
+        offs = [0]
+        for m in msgs:
+            offs.append(offs[-1] + len(m))
+        off = (ctypes.c_uint64 * (n + 1))(*offs)
+        ok = ctypes.c_int(0)
+        self._chk(self._L.bgls_verify_aggregate_signature(self._h, curve, b"".join(msgs), off, n, keys, sig,
+                                                          1 if allow_duplicates else 0, ctypes.byref(ok)))
+        return bool(ok.value)
+
+    def verify_aggregate_signature_ptr(self, curve, h_msgs: int, h_offsets: int, n: int, h_keys: int, h_sig: int, allow_duplicates: bool = False) -> bool:
+        """Same call on raw host pointers (pinned buffers of the bench)."""
+        ok = ctypes.c_int(0)
+        self._chk(self._L.bgls_verify_aggregate_signature(self._h, curve, ctypes.c_char_p(h_msgs), ctypes.cast(h_offsets, ctypes.POINTER(ctypes.c_uint64)),
+                                                          n, ctypes.c_char_p(h_keys), ctypes.c_char_p(h_sig), 1 if allow_duplicates else 0, ctypes.byref(ok)))
+        return bool(ok.value)
 
     def compress_points(self, curve, group, pts: bytes, n: int) -> bytes:
         """n uncompressed records -> n compressed records (Point.Marshal)."""

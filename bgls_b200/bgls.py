@@ -64,7 +64,11 @@ def verifyAggSig(curve: CurveSystem, aggsig: Point, keys, msgs, allowDuplicates:
         return False
     if not allowDuplicates and containsDuplicateMessage(msgs):
         return False
-    # the reference hashes in n goroutines (bgls.go:106-111); the default hash is one kernel launch for all messages
+    if hash is None and all(curve._is(k, 2) for k in keys) and curve._is(aggsig, 1):
+        # default hash: the whole function is one engine call (bgls_verify_aggregate_signature); the duplicate check
+        # above is repeated there only when allowDuplicates is false, with the same verdict
+        return curve._ctx().verify_aggregate_signature(curve.cid, [bytes(m) for m in msgs], b"".join(k._canon() for k in keys),
+                                                       aggsig._canon(), allow_duplicates=True)
     hashed = curve.HashToG1Many(msgs) if hash is None else [hash(m) for m in msgs]
     pts1 = hashed + [aggsig.Mul(-1)]
     pts2 = list(keys) + [curve.GetG2()]

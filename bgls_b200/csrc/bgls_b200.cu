@@ -16,6 +16,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/bgls_b200.h"
@@ -1152,6 +1153,72 @@ int bgls_hash_to_g1_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void
     if (!ctx || !curve_ok(curve) || (n && (!d_offsets || !d_out))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     return hash_dev(ctx, curve, d_msgs, d_offsets, n, d_out, (cudaStream_t)stream);
+}
+// ---- verifyAggSig as one call (bgls/bgls.go:94-119)
+// G2 generators (curves/altbn128_test.go:26-35, curves/bls12_381.go:328-346) and field primes, wire form (big-endian)
+static const uint8_t kG2GenBN254[128] = {0x19, 0x8e, 0x93, 0x93, 0x92, 0x0d, 0x48, 0x3a, 0x72, 0x60, 0xbf, 0xb7, 0x31, 0xfb, 0x5d, 0x25, 0xf1, 0xaa, 0x49, 0x33, 0x35, 0xa9, 0xe7, 0x12, 0x97, 0xe4, 0x85, 0xb7, 0xae, 0xf3, 0x12, 0xc2, 0x18, 0x00, 0xde, 0xef, 0x12, 0x1f, 0x1e, 0x76, 0x42, 0x6a, 0x00, 0x66, 0x5e, 0x5c, 0x44, 0x79, 0x67, 0x43, 0x22, 0xd4, 0xf7, 0x5e, 0xda, 0xdd, 0x46, 0xde, 0xbd, 0x5c, 0xd9, 0x92, 0xf6, 0xed, 0x09, 0x06, 0x89, 0xd0, 0x58, 0x5f, 0xf0, 0x75, 0xec, 0x9e, 0x99, 0xad, 0x69, 0x0c, 0x33, 0x95, 0xbc, 0x4b, 0x31, 0x33, 0x70, 0xb3, 0x8e, 0xf3, 0x55, 0xac, 0xda, 0xdc, 0xd1, 0x22, 0x97, 0x5b, 0x12, 0xc8, 0x5e, 0xa5, 0xdb, 0x8c, 0x6d, 0xeb, 0x4a, 0xab, 0x71, 0x80, 0x8d, 0xcb, 0x40, 0x8f, 0xe3, 0xd1, 0xe7, 0x69, 0x0c, 0x43, 0xd3, 0x7b, 0x4c, 0xe6, 0xcc, 0x01, 0x66, 0xfa, 0x7d, 0xaa};
+static const uint8_t kG2GenBLS381[192] = {0x13, 0xe0, 0x2b, 0x60, 0x52, 0x71, 0x9f, 0x60, 0x7d, 0xac, 0xd3, 0xa0, 0x88, 0x27, 0x4f, 0x65, 0x59, 0x6b, 0xd0, 0xd0, 0x99, 0x20, 0xb6, 0x1a, 0xb5, 0xda, 0x61, 0xbb, 0xdc, 0x7f, 0x50, 0x49, 0x33, 0x4c, 0xf1, 0x12, 0x13, 0x94, 0x5d, 0x57, 0xe5, 0xac, 0x7d, 0x05, 0x5d, 0x04, 0x2b, 0x7e, 0x02, 0x4a, 0xa2, 0xb2, 0xf0, 0x8f, 0x0a, 0x91, 0x26, 0x08, 0x05, 0x27, 0x2d, 0xc5, 0x10, 0x51, 0xc6, 0xe4, 0x7a, 0xd4, 0xfa, 0x40, 0x3b, 0x02, 0xb4, 0x51, 0x0b, 0x64, 0x7a, 0xe3, 0xd1, 0x77, 0x0b, 0xac, 0x03, 0x26, 0xa8, 0x05, 0xbb, 0xef, 0xd4, 0x80, 0x56, 0xc8, 0xc1, 0x21, 0xbd, 0xb8, 0x06, 0x06, 0xc4, 0xa0, 0x2e, 0xa7, 0x34, 0xcc, 0x32, 0xac, 0xd2, 0xb0, 0x2b, 0xc2, 0x8b, 0x99, 0xcb, 0x3e, 0x28, 0x7e, 0x85, 0xa7, 0x63, 0xaf, 0x26, 0x74, 0x92, 0xab, 0x57, 0x2e, 0x99, 0xab, 0x3f, 0x37, 0x0d, 0x27, 0x5c, 0xec, 0x1d, 0xa1, 0xaa, 0xa9, 0x07, 0x5f, 0xf0, 0x5f, 0x79, 0xbe, 0x0c, 0xe5, 0xd5, 0x27, 0x72, 0x7d, 0x6e, 0x11, 0x8c, 0xc9, 0xcd, 0xc6, 0xda, 0x2e, 0x35, 0x1a, 0xad, 0xfd, 0x9b, 0xaa, 0x8c, 0xbd, 0xd3, 0xa7, 0x6d, 0x42, 0x9a, 0x69, 0x51, 0x60, 0xd1, 0x2c, 0x92, 0x3a, 0xc9, 0xcc, 0x3b, 0xac, 0xa2, 0x89, 0xe1, 0x93, 0x54, 0x86, 0x08, 0xb8, 0x28, 0x01};
+static const uint8_t kPrimeBN254[32] = {0x30, 0x64, 0x4e, 0x72, 0xe1, 0x31, 0xa0, 0x29, 0xb8, 0x50, 0x45, 0xb6, 0x81, 0x81, 0x58, 0x5d, 0x97, 0x81, 0x6a, 0x91, 0x68, 0x71, 0xca, 0x8d, 0x3c, 0x20, 0x8c, 0x16, 0xd8, 0x7c, 0xfd, 0x47};
+static const uint8_t kPrimeBLS381[48] = {0x1a, 0x01, 0x11, 0xea, 0x39, 0x7f, 0xe6, 0x9a, 0x4b, 0x1b, 0xa7, 0xb6, 0x43, 0x4b, 0xac, 0xd7, 0x64, 0x77, 0x4b, 0x84, 0xf3, 0x85, 0x12, 0xbf, 0x67, 0x30, 0xd2, 0xa0, 0xf6, 0xb0, 0xf6, 0x24, 0x1e, 0xab, 0xff, 0xfe, 0xb1, 0x53, 0xff, 0xff, 0xb9, 0xfe, 0xff, 0xff, 0xff, 0xff, 0xaa, 0xab};
+
+// y -> q - y on a big-endian field element (Point.Mul(-1) of the aggregate signature, bgls/bgls.go:112); 0 stays 0
+static void be_negate(uint8_t* y, const uint8_t* q, size_t F) {
+    bool zero = true;
+    for (size_t i = 0; i < F; i++) zero = zero && y[i] == 0;
+    if (zero) return;
+    int borrow = 0;
+    for (size_t i = F; i-- > 0;) {
+        int d = (int)q[i] - (int)y[i] - borrow;
+        borrow = d < 0;
+        y[i] = (uint8_t)(d + (borrow ? 256 : 0));
+    }
+}
+int bgls_verify_aggregate_signature(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                    const uint8_t* keys, const uint8_t* sig, int allow_duplicates, int* ok) {
+    if (!ctx || !curve_ok(curve) || !offsets || !sig || !ok || (n && !keys)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, BGLS_ERR_ARG, "offsets not monotone");
+    const size_t total = offsets[n] - offsets[0];
+    if (total && !msgs) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    *ok = 0;
+    if (!allow_duplicates) {   // containsDuplicateMessage, bgls/bgls.go:98-102,139-150: the verdict is false before any pairing
+        std::unordered_set<std::string> seen;
+        seen.reserve(n * 2);
+        const char* base = msgs ? (const char*)msgs : "";
+        for (size_t i = 0; i < n; i++)
+            if (!seen.emplace(base + (total ? offsets[i] : 0), offsets[i + 1] - offsets[i]).second) return BGLS_OK;
+    }
+    SlotLock sl(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), np = n + 1;
+    const size_t bm = align_up(total + 16), bo = align_up((n + 1) * 8), b1 = align_up(np * 2 * F), b2 = align_up(np * 4 * F);
+    const size_t bout = align_up(12 * F + 16), bw = pairing_work_bytes(ctx, curve, np);
+    int rc = ensure_scratch(ctx, sl.s, bm + bo + b1 + b2 + bout + bw);
+    if (rc) return rc;
+    uint8_t* dm = (uint8_t*)sl.s->scratch;
+    uint8_t *doff = dm + bm, *d1 = doff + bo, *d2 = d1 + b1, *dout = d2 + b2, *work = dout + bout;
+    int* dflag = (int*)(dout + 12 * F);
+    cudaStream_t s = sl.s->stream;
+    std::vector<uint64_t> rel(n + 1);
+    for (size_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+    uint8_t tail[2 * 48];   // -sigma
+    memcpy(tail, sig, 2 * F);
+    const bool sig_inf = (curve == BGLS_BLS12_381) && (tail[0] & 0x40);
+    if (!sig_inf) be_negate(tail + F, curve == BGLS_ALTBN128 ? kPrimeBN254 : kPrimeBLS381, F);
+    if (total) CU(cudaMemcpyAsync(dm, msgs + offsets[0], total, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(doff, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (n) CU(cudaMemcpyAsync(d2, keys, n * 4 * F, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d2 + n * 4 * F, curve == BGLS_ALTBN128 ? kG2GenBN254 : kG2GenBLS381, 4 * F, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d1 + n * 2 * F, tail, 2 * F, cudaMemcpyHostToDevice, s));
+    rc = hash_dev(ctx, curve, dm, doff, n, d1, s);                       // pts1[i] = HashToG1(msgs[i]), bgls.go:106-111
+    if (rc) return rc;
+    rc = pairing_dev(ctx, curve, d1, d2, np, 1, dout, dflag, work, s);    // PairingProduct(pts1, pts2), bgls.go:114
+    if (rc) return rc;
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));   // also keeps `rel` and `tail` alive until the copies are done
+    *ok = flag;                     // aggPt.Equals(GetGTIdentity()), bgls.go:115-118
+    return BGLS_OK;
 }
 int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, const uint64_t* offsets,
                              size_t nbatch, uint8_t* out_ok) {

@@ -129,6 +129,16 @@ int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish);
 /* measured full-rate IMAD.WIDE.U32 throughput of this GPU (32x32+64 multiply-accumulates / s) */
 int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s);
 
+/* verifyAggSig -- bgls/bgls.go:94-119, the body of VerifyAggregateSignature (bgls.go:82-84, allow_duplicates = 0) and
+ * KoskVerifyAggregateSignature / DistinctMsgVerifyAggregateSignature (allow_duplicates = 1; the caller prepends the
+ * 0x01 byte / the public key to each message as bgls/blsKosk.go:100-106 and blsDistinctMessage.go:45-57 do).
+ * Message i is msgs[offsets[i] .. offsets[i+1]); keys: n uncompressed G2 records; sig: one uncompressed G1 record.
+ * One call does what the reference does in n goroutines plus PairingProduct: the duplicate-message check on the host
+ * (bgls.go:139-150: a duplicate makes the verdict false before any pairing), HashToG1 of every message, sigma -> -sigma,
+ * the (n+1)-pair product against [keys..., g2] and the comparison with the GT identity.  *ok = 1 iff it verifies. */
+int bgls_verify_aggregate_signature(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                    const uint8_t* keys, const uint8_t* sig, int allow_duplicates, int* ok);
+
 /* Point.Marshal (compressed form) -- curves/altbn128.go:81-89 (G1), :203-221 (G2); curves/bls12_381.go:57-59,118-120.
  * pts: n uncompressed records; out: n compressed records of F (G1) / 2F (G2) bytes.
  *   altbn128: x, bit 7 of byte 0 set iff 2y > q; G2 = x_im || x_re with one sign bit per y component.

@@ -354,3 +354,38 @@ def test_compressed_wire_formats(ctx, cid, c):
         q, ok = un(p.MarshalUncompressed())
         assert ok and q.Equals(p)
         assert un(p.Marshal()[:-1]) == (None, False)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_verify_aggregate_signature_entry_point(ctx, cid, c):
+    """bgls_verify_aggregate_signature = verifyAggSig (bgls/bgls.go:94-119) in one call: accept / reject cases of
+    bgls/bgls_test.go:40-77 with real HashToG1 points from the oracle, the n = 0 quirk, an infinity signature,
+    ragged and empty messages, and the duplicate-message rule."""
+    rng = random.Random(555 + cid)
+    n = 9
+    msgs = [bytes(rng.randrange(256) for _ in range(ln)) for ln in (32, 0, 1, 64, 31, 33, 100, 7, 32)]
+    sks = [rng.randrange(1, c.r) for _ in range(n)]
+    hs = [c.hash_to_g1(m) for m in msgs]
+    pks = [c.g2_mul(c.g2, k) for k in sks]
+    sigma = None
+    for h, k in zip(hs, sks):
+        sigma = c.g1_add(sigma, c.g1_mul(h, k))
+    keys = b"".join(c.marshal_g2(q) for q in pks)
+    sig = c.marshal_g1(sigma)
+    V = ctx.verify_aggregate_signature
+    assert V(cid, msgs, keys, sig) is True
+    assert V(cid, msgs[::-1], keys, sig) is False                                   # swapped messages
+    assert V(cid, msgs[:-1], keys[:-4 * c.nbytes], sig) is False                    # a signer dropped
+    assert V(cid, msgs, keys, c.marshal_g1(c.g1_add(sigma, c.g1))) is False         # wrong signature
+    # duplicate message: rejected before any pairing unless duplicates are allowed (Kosk / DistinctMsg callers)
+    m2 = msgs[:-1] + [msgs[0]]
+    sig2 = None
+    for m, k in zip(m2, sks):
+        sig2 = c.g1_add(sig2, c.g1_mul(c.hash_to_g1(m), k))
+    assert V(cid, m2, keys, c.marshal_g1(sig2)) is False
+    assert V(cid, m2, keys, c.marshal_g1(sig2), allow_duplicates=True) is True
+    # n = 0: the product is the single pair (-sigma, g2): true iff sigma is the point at infinity (bgls.go:103-114)
+    assert V(cid, [], b"", c.marshal_g1(None)) is True
+    assert V(cid, [], b"", c.marshal_g1(c.g1)) is False
+    # single signer
+    assert V(cid, msgs[:1], keys[:4 * c.nbytes], c.marshal_g1(c.g1_mul(hs[0], sks[0]))) is True
