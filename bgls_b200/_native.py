@@ -20,7 +20,7 @@ EXPORTS = [
     "bgls_pairing_check_batch", "bgls_pairing_product_dev", "bgls_miller_product_dev", "bgls_final_exp_product_dev",
     "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_hash_to_g1", "bgls_hash_to_g1_dev", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
     "bgls_compress_points", "bgls_compress_points_dev", "bgls_decompress_points", "bgls_decompress_points_dev",
-    "bgls_verify_aggregate_signature",
+    "bgls_verify_aggregate_signature", "bgls_verify_multi_signature",
 ]
 
 _lib = None
@@ -66,6 +66,7 @@ def load():
     L.bgls_decompress_points.argtypes = [vp, i, i, cp, sz, i, cp, cp]
     L.bgls_decompress_points_dev.argtypes = [vp, i, i, vp, sz, i, vp, vp, vp]
     L.bgls_verify_aggregate_signature.argtypes = [vp, i, cp, ctypes.POINTER(ctypes.c_uint64), sz, cp, cp, i, ip]
+    L.bgls_verify_multi_signature.argtypes = [vp, i, cp, sz, cp, sz, cp, ip]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
     L.bgls_set_profiling.argtypes = [vp, i]
@@ -159,6 +160,12 @@ class Context:
         ok = ctypes.c_int(0)
         self._chk(self._L.bgls_verify_aggregate_signature(self._h, curve, b"".join(msgs), off, n, keys, sig,
                                                           1 if allow_duplicates else 0, ctypes.byref(ok)))
+        return bool(ok.value)
+
+    def verify_multi_signature(self, curve, msg: bytes, keys: bytes, n: int, sig: bytes) -> bool:
+        """verifyMultiSignature (bgls/bgls.go:89-92) in one engine call."""
+        ok = ctypes.c_int(0)
+        self._chk(self._L.bgls_verify_multi_signature(self._h, curve, msg, len(msg), keys, n, sig, ctypes.byref(ok)))
         return bool(ok.value)
 
     def verify_aggregate_signature_ptr(self, curve, h_msgs: int, h_offsets: int, n: int, h_keys: int, h_sig: int, allow_duplicates: bool = False) -> bool:

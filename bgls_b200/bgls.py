@@ -55,6 +55,9 @@ def VerifyAggregateSignature(curve: CurveSystem, aggsig: Point, keys, msgs) -> b
 
 
 def verifyMultiSignature(curve: CurveSystem, aggsig: Point, keys, msg: bytes, hash=None) -> bool:
+    if hash is None and len(keys) >= 1 and all(curve._is(k, 2) for k in keys) and curve._is(aggsig, 1):
+        # default hash: one engine call (bgls_verify_multi_signature)
+        return curve._ctx().verify_multi_signature(curve.cid, bytes(msg), b"".join(k._canon() for k in keys), len(keys), aggsig._canon())
     vs = AggregatePoints(keys)
     return VerifySingleSignatureCustHash(curve, aggsig, vs, msg, hash or curve.HashToG1)
 

@@ -374,6 +374,8 @@ struct MachDev {
 // Device-resident calls are keyed by the caller's stream, so work enqueued on different streams never shares scratch.
 struct Slot {
     cudaStream_t stream = nullptr;   // the slot's own stream (host-buffer calls)
+    cudaStream_t aux = nullptr;      // second stream for independent work inside one call (fork / join events below)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t owner = nullptr;    // caller stream this slot's scratch is currently ordered on (device-resident calls)
     bool owned = false;
     void* scratch = nullptr;
@@ -854,10 +856,20 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     bgls_ctx* ctx = new bgls_ctx();
     ctx->device = device;
     bool ok = cudaSetDevice(device) == cudaSuccess;
-    for (int i = 0; ok && i < NSLOT; i++) ok = cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < NSLOT; i++) {
+        Slot& sl = ctx->slots[i];
+        ok = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&sl.aux, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) {
-        for (auto& sl : ctx->slots)
+        for (auto& sl : ctx->slots) {
             if (sl.stream) cudaStreamDestroy(sl.stream);
+            if (sl.aux) cudaStreamDestroy(sl.aux);
+            if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
+            if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+        }
         delete ctx;
         return BGLS_ERR_CUDA;
     }
@@ -885,6 +897,9 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
     for (auto& sl : ctx->slots) {
         if (sl.scratch) cudaFree(sl.scratch);
         if (sl.stream) cudaStreamDestroy(sl.stream);
+        if (sl.aux) cudaStreamDestroy(sl.aux);
+        if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
+        if (sl.ev_join) cudaEventDestroy(sl.ev_join);
     }
     for (auto& d : ctx->mach)
         if (d.blob) cudaFree(d.blob);
@@ -1218,6 +1233,51 @@ int bgls_verify_aggregate_signature(bgls_ctx* ctx, int curve, const uint8_t* msg
     CU(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));   // also keeps `rel` and `tail` alive until the copies are done
     *ok = flag;                     // aggPt.Equals(GetGTIdentity()), bgls.go:115-118
+    return BGLS_OK;
+}
+int bgls_verify_multi_signature(bgls_ctx* ctx, int curve, const uint8_t* msg, size_t msg_len, const uint8_t* keys, size_t n,
+                                const uint8_t* sig, int* ok) {
+    if (!ctx || !curve_ok(curve) || !keys || !sig || !ok || n == 0 || (msg_len && !msg)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    *ok = 0;
+    SlotLock sl(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve);
+    const size_t bm = align_up(msg_len + 16), bo = align_up(16), bk = align_up(n * 4 * F), b1 = align_up(2 * 2 * F), b2 = align_up(2 * 4 * F);
+    const size_t bout = align_up(12 * F + 16);
+    const size_t bw = std::max(agg_work_bytes(curve, 2, n), pairing_work_bytes(ctx, curve, 2));
+    int rc = ensure_scratch(ctx, sl.s, bm + bo + bk + b1 + b2 + bout + bw);
+    if (rc) return rc;
+    uint8_t* dm = (uint8_t*)sl.s->scratch;
+    uint8_t *doff = dm + bm, *dk = doff + bo, *d1 = dk + bk, *d2 = d1 + b1, *dout = d2 + b2, *work = dout + bout;
+    int* dflag = (int*)(dout + 12 * F);
+    cudaStream_t s = sl.s->stream;
+    const uint64_t rel[2] = {0, (uint64_t)msg_len};
+    uint8_t tail[2 * 48];
+    memcpy(tail, sig, 2 * F);
+    // the reference checks e(-H(m), vs) e(sigma, g2) == 1 (bgls.go:65-70); e(H(m), vs) e(-sigma, g2) is its inverse, so
+    // the verdict is the same and the negation is one field subtraction on the host
+    if (!((curve == BGLS_BLS12_381) && (tail[0] & 0x40))) be_negate(tail + F, curve == BGLS_ALTBN128 ? kPrimeBN254 : kPrimeBLS381, F);
+    if (msg_len) CU(cudaMemcpyAsync(dm, msg, msg_len, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(doff, rel, 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dk, keys, n * 4 * F, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d1 + 2 * F, tail, 2 * F, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d2 + 4 * F, curve == BGLS_ALTBN128 ? kG2GenBN254 : kG2GenBLS381, 4 * F, cudaMemcpyHostToDevice, s));
+    // the hash of the message (one long dependent chain) and the key aggregation are independent: fork the hash onto
+    // the slot's second stream and join before the pairing
+    CU(cudaEventRecord(sl.s->ev_fork, s));
+    CU(cudaStreamWaitEvent(sl.s->aux, sl.s->ev_fork, 0));
+    rc = hash_dev(ctx, curve, dm, doff, 1, d1, sl.s->aux);         // HashToG1(msg), bgls.go:67
+    if (rc) return rc;
+    CU(cudaEventRecord(sl.s->ev_join, sl.s->aux));
+    rc = aggregate_dev(ctx, curve, 2, dk, n, d2, work, s);        // vs = AggregatePoints(keys), bgls.go:90
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(s, sl.s->ev_join, 0));
+    rc = pairing_dev(ctx, curve, d1, d2, 2, 1, dout, dflag, work, s);
+    if (rc) return rc;
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *ok = flag;
     return BGLS_OK;
 }
 int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, const uint64_t* offsets,

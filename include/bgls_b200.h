@@ -139,6 +139,12 @@ int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s);
 int bgls_verify_aggregate_signature(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_t* offsets, size_t n,
                                     const uint8_t* keys, const uint8_t* sig, int allow_duplicates, int* ok);
 
+/* verifyMultiSignature -- bgls/bgls.go:89-92 (exported as KoskVerifyMultiSignature, bgls/blsKosk.go:117-120, whose caller
+ * prepends the 0x01 byte to the message): vs = AggregatePoints(keys) over n >= 1 uncompressed G2 records, then the
+ * single-signature check of bgls.go:65-70 on HashToG1(msg).  *ok = 1 iff it verifies. */
+int bgls_verify_multi_signature(bgls_ctx* ctx, int curve, const uint8_t* msg, size_t msg_len, const uint8_t* keys, size_t n,
+                                const uint8_t* sig, int* ok);
+
 /* Point.Marshal (compressed form) -- curves/altbn128.go:81-89 (G1), :203-221 (G2); curves/bls12_381.go:57-59,118-120.
  * pts: n uncompressed records; out: n compressed records of F (G1) / 2F (G2) bytes.
  *   altbn128: x, bit 7 of byte 0 set iff 2y > q; G2 = x_im || x_re with one sign bit per y component.

@@ -389,3 +389,20 @@ def test_verify_aggregate_signature_entry_point(ctx, cid, c):
     assert V(cid, [], b"", c.marshal_g1(c.g1)) is False
     # single signer
     assert V(cid, msgs[:1], keys[:4 * c.nbytes], c.marshal_g1(c.g1_mul(hs[0], sks[0]))) is True
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_verify_multi_signature_entry_point(ctx, cid, c):
+    """bgls_verify_multi_signature = verifyMultiSignature (bgls/bgls.go:89-92): bgls/blsKosk_test.go:35-64 shape."""
+    rng = random.Random(808 + cid)
+    msg = b"\x01" + bytes(rng.randrange(256) for _ in range(64))
+    h = c.hash_to_g1(msg)
+    for n in (1, 2, 8, 37):
+        sks = [rng.randrange(1, c.r) for _ in range(n)]
+        keys = b"".join(c.marshal_g2(c.g2_mul(c.g2, k)) for k in sks)
+        sig = c.marshal_g1(c.g1_mul(h, sum(sks) % c.r))
+        assert ctx.verify_multi_signature(cid, msg, keys, n, sig) is True
+        assert ctx.verify_multi_signature(cid, msg + b"x", keys, n, sig) is False
+        if n > 1:
+            assert ctx.verify_multi_signature(cid, msg, keys[4 * c.nbytes:], n - 1, sig) is False
+        assert ctx.verify_multi_signature(cid, msg, keys, n, c.marshal_g1(c.g1_add(c.unmarshal_g1(sig), c.g1))) is False

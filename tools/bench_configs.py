@@ -57,6 +57,25 @@ def main():
     want = ctx.scale_points(cid, 2, curve.GetG2().raw, to_b([sum(ks) % r]), 1)
     assert bytes(d_sum.cpu().numpy()) == want, "aggregate differs from (sum k_i) G2"
     out["config3_g2_aggregate"] = {"keys": n, "ms": ms, "keys_per_s": n / (ms * 1e-3), "GB_per_s": n * 192 / (ms * 1e-3) / 1e9}
+    # the whole verifyMultiSignature (bgls/bgls.go:89-92) through bgls_verify_multi_signature: pinned host buffers in, verdict out
+    import ctypes
+    import time
+    msg = b"\x01" + bytes(range(64))
+    H = ctx.hash_to_g1(cid, [msg])
+    sig = ctx.scale_points(cid, 1, H, to_b([sum(ks) % r]), 1)
+    h_keys = torch.frombuffer(bytearray(keys), dtype=torch.uint8).pin_memory()
+    ok = ctypes.c_int(0)
+
+    def multisig():
+        rc = ctx._L.bgls_verify_multi_signature(ctx._h, cid, msg, len(msg), ctypes.c_char_p(h_keys.data_ptr()), n, sig, ctypes.byref(ok))
+        assert rc == 0 and ok.value == 1
+    multisig()
+    t0 = time.perf_counter()
+    for _ in range(args.reps):
+        multisig()
+    dt = (time.perf_counter() - t0) / args.reps
+    out["config3_verify_multi_signature_e2e"] = {"keys": n, "ms": dt * 1e3, "h2d_bytes": len(keys) + len(msg) + len(sig),
+                                                 "api": "bgls_verify_multi_signature (pinned host buffers)"}
 
     # ---- config 5
     cid, curve, r = 0, Altbn128, 21888242871839275222246405745257275088548364400416034343698204186575808495617
