@@ -21,6 +21,8 @@ EXPORTS = [
     "bgls_aggregate_points_dev", "bgls_scale_points_dev", "bgls_pairing_check_batch_dev", "bgls_launch_count", "bgls_hash_to_g1", "bgls_hash_to_g1_dev", "bgls_set_profiling", "bgls_last_kernel_ms", "bgls_intpipe_peak",
     "bgls_compress_points", "bgls_compress_points_dev", "bgls_decompress_points", "bgls_decompress_points_dev",
     "bgls_verify_aggregate_signature", "bgls_verify_multi_signature",
+    "bgls_exchange_create", "bgls_exchange_connect", "bgls_exchange_error", "bgls_miller_product_exchange_dev",
+    "bgls_final_exp_exchanged_dev",
 ]
 
 _lib = None
@@ -67,6 +69,11 @@ def load():
     L.bgls_decompress_points_dev.argtypes = [vp, i, i, vp, sz, i, vp, vp, vp]
     L.bgls_verify_aggregate_signature.argtypes = [vp, i, cp, ctypes.POINTER(ctypes.c_uint64), sz, cp, cp, i, ip]
     L.bgls_verify_multi_signature.argtypes = [vp, i, cp, sz, cp, sz, cp, ip]
+    L.bgls_exchange_create.argtypes = [vp, i, i, i, cp]
+    L.bgls_exchange_connect.argtypes = [vp, i, cp]
+    L.bgls_exchange_error.argtypes = [vp, ip]
+    L.bgls_miller_product_exchange_dev.argtypes = [vp, i, vp, vp, sz, i, ctypes.c_uint64, vp]
+    L.bgls_final_exp_exchanged_dev.argtypes = [vp, i, i, ctypes.c_uint64, vp, vp, vp]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
     L.bgls_set_profiling.argtypes = [vp, i]
@@ -219,6 +226,26 @@ class Context:
         return [bool(b) for b in out.raw[:nb]]
 
     # ---- device-resident API (raw device pointers + cudaStream_t handles as ints)
+    # ---- peer-memory exchange (multi-GPU)
+    def exchange_create(self, world: int, rank: int, lanes: int) -> bytes:
+        h = ctypes.create_string_buffer(64)
+        self._chk(self._L.bgls_exchange_create(self._h, world, rank, lanes, h))
+        return h.raw
+
+    def exchange_connect(self, peer_rank: int, handle: bytes):
+        self._chk(self._L.bgls_exchange_connect(self._h, peer_rank, handle))
+
+    def exchange_error(self) -> int:
+        e = ctypes.c_int(0)
+        self._chk(self._L.bgls_exchange_error(self._h, ctypes.byref(e)))
+        return e.value
+
+    def miller_product_exchange_dev(self, curve, d_g1, d_g2, n, lane, epoch, stream):
+        self._chk(self._L.bgls_miller_product_exchange_dev(self._h, curve, d_g1, d_g2, n, lane, epoch, stream))
+
+    def final_exp_exchanged_dev(self, curve, lane, epoch, d_out, d_flag, stream):
+        self._chk(self._L.bgls_final_exp_exchanged_dev(self._h, curve, lane, epoch, d_out, d_flag, stream))
+
     def pairing_product_dev(self, curve, d_g1, d_g2, n, d_out, d_flag, stream):
         self._chk(self._L.bgls_pairing_product_dev(self._h, curve, d_g1, d_g2, n, d_out, d_flag, stream))
 

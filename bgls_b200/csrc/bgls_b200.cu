@@ -313,6 +313,37 @@ __global__ void __launch_bounds__(TB) k_hash_to_g1_bls(const uint8_t* __restrict
     }
 }
 
+// ---------------------------------------------------------------- peer-memory exchange of the per-GPU partials
+// Every rank stores its 12F-byte Miller product straight into a mailbox on each peer (NVLink peer memory mapped
+// through CUDA IPC) and then raises that mailbox's epoch flag; the finishing side waits for the flags of all ranks.
+// Slots are double-buffered by epoch parity (a rank can be one step ahead on the same lane, never two).
+template <class PP>
+__global__ void __launch_bounds__(256) k_exchange_send_t(const uint8_t* __restrict__ partial, int nbytes, PP pp, int world, unsigned long long epoch) {
+    for (int idx = threadIdx.x; idx < world * nbytes; idx += blockDim.x) {
+        const int r = idx / nbytes, b = idx % nbytes;
+        pp.slot[r][b] = partial[b];
+    }
+    __threadfence_system();   // the payload is visible to every peer before any flag is
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        *(volatile unsigned long long*)pp.flag[threadIdx.x] = epoch;
+        __threadfence_system();
+    }
+}
+// one thread per rank polls its flag; bounded, so a missing peer reports an error instead of hanging the GPU
+__global__ void __launch_bounds__(32) k_exchange_wait(const unsigned long long* flags, int world, unsigned long long epoch,
+                                                     int* __restrict__ err) {
+    if ((int)threadIdx.x < world) {
+        const volatile unsigned long long* f = flags + threadIdx.x;
+        long long spins = 0;
+        while (*f < epoch) {
+            if (++spins > (1ll << 27)) { *err = 1; break; }   // several seconds
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+
 // compressed wire formats, one point per thread (codec.cuh)
 template <class C, int G>
 __global__ void __launch_bounds__(TB) k_compress(const uint8_t* __restrict__ pts, size_t n, uint8_t* __restrict__ out) {
@@ -384,8 +415,21 @@ struct Slot {
 };
 constexpr int NSLOT = 8;
 
+// peer-memory exchange state (bgls_exchange_*): this rank's mailbox and the mapped mailboxes of the peers
+struct Exchange {
+    int world = 0, rank = 0, lanes = 0;
+    uint8_t* local = nullptr;                 // [lanes][2][world] records of XREC bytes, then [lanes][2][world] flags
+    std::vector<uint8_t*> peer;               // base pointers of every rank's mailbox (own rank: local)
+    uint8_t** d_slot = nullptr;               // device tables [lanes][2][world]: where MY record lives in rank r's mailbox
+    unsigned long long** d_flag = nullptr;
+    int* d_err = nullptr;
+    bool ready = false;
+};
+constexpr size_t XREC = 640;                  // 12 * 48 bytes rounded up to a multiple of 128
+
 struct bgls_ctx {
     MachDev mach[2];
+    Exchange xch;
     Slot slots[NSLOT];
     std::atomic<unsigned> rr{0};
     std::mutex own_mu;
@@ -903,6 +947,10 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
     }
     for (auto& d : ctx->mach)
         if (d.blob) cudaFree(d.blob);
+    for (int r = 0; r < (int)ctx->xch.peer.size(); r++)
+        if (ctx->xch.peer[r] && r != ctx->xch.rank) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
+    if (ctx->xch.local) cudaFree(ctx->xch.local);
+    if (ctx->xch.d_err) cudaFree(ctx->xch.d_err);
     for (int i = 0; i < 3; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
@@ -1334,6 +1382,103 @@ int bgls_miller_product_dev(bgls_ctx* ctx, int curve, const void* d_g1, const vo
     int rc = dev_work(ctx, sl.s, pairing_work_bytes(ctx, curve, n), &work);
     if (rc) return rc;
     return pairing_dev(ctx, curve, d_g1, d_g2, n, 0, d_out_f, nullptr, work, (cudaStream_t)stream);
+}
+// ---- peer-memory exchange (multi-GPU, one process per GPU): see k_exchange_send / k_exchange_wait
+struct PeerPtrs {
+    uint8_t* slot[8];
+    unsigned long long* flag[8];
+};
+static size_t xch_rec_off(const Exchange& x, int lane, int parity, int r, size_t rec) {
+    return ((size_t)(lane * 2 + parity) * x.world + r) * rec;
+}
+static size_t xch_flag_base(const Exchange& x) { return align_up((size_t)x.lanes * 2 * x.world * 576, 256); }
+static size_t xch_flag_off(const Exchange& x, int lane, int parity, int r) {
+    return xch_flag_base(x) + ((size_t)(lane * 2 + parity) * x.world + r) * sizeof(unsigned long long);
+}
+int bgls_exchange_create(bgls_ctx* ctx, int world, int rank, int lanes, uint8_t* handle_out) {
+    if (!ctx || !handle_out || world < 1 || world > 8 || rank < 0 || rank >= world || lanes < 1 || lanes > 64) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Exchange& x = ctx->xch;
+    if (x.local) return fail(ctx, BGLS_ERR_ARG, "exchange already created");
+    CU(cudaSetDevice(ctx->device));
+    x.world = world; x.rank = rank; x.lanes = lanes;
+    const size_t bytes = xch_flag_base(x) + (size_t)lanes * 2 * world * sizeof(unsigned long long);
+    CU(cudaMalloc((void**)&x.local, bytes));
+    CU(cudaMemset(x.local, 0, bytes));
+    CU(cudaMalloc((void**)&x.d_err, sizeof(int)));
+    CU(cudaMemset(x.d_err, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, x.local));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, sizeof(h));
+    x.peer.assign(world, nullptr);
+    x.peer[rank] = x.local;
+    x.ready = world == 1;
+    return BGLS_OK;
+}
+int bgls_exchange_connect(bgls_ctx* ctx, int peer_rank, const uint8_t* handle) {
+    if (!ctx || !handle || !ctx->xch.local || peer_rank < 0 || peer_rank >= ctx->xch.world) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    Exchange& x = ctx->xch;
+    CU(cudaSetDevice(ctx->device));
+    if (peer_rank != x.rank && !x.peer[peer_rank]) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof(h));
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x.peer[peer_rank] = (uint8_t*)p;
+    }
+    bool all = true;
+    for (uint8_t* q : x.peer) all = all && q != nullptr;
+    x.ready = all;
+    return BGLS_OK;
+}
+int bgls_exchange_error(bgls_ctx* ctx, int* err) {
+    if (!ctx || !err || !ctx->xch.d_err) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(err, ctx->xch.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    return BGLS_OK;
+}
+int bgls_miller_product_exchange_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int lane,
+                                     uint64_t epoch, void* stream) {
+    if (!ctx || !curve_ok(curve) || (n && (!d_g1 || !d_g2)) || !ctx->xch.ready || lane < 0 || lane >= ctx->xch.lanes || epoch == 0)
+        return fail(ctx, BGLS_ERR_ARG, "bad argument / exchange not connected");
+    Exchange& x = ctx->xch;
+    SlotLock sl(ctx, (cudaStream_t)stream);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), rec = 12 * F, bw = pairing_work_bytes(ctx, curve, n);
+    void* work;
+    int rc = dev_work(ctx, sl.s, bw + align_up(rec + 16), &work);
+    if (rc) return rc;
+    uint8_t* partial = (uint8_t*)work + bw;
+    rc = pairing_dev(ctx, curve, d_g1, d_g2, n, 0, partial, nullptr, work, (cudaStream_t)stream);
+    if (rc) return rc;
+    PeerPtrs pp{};
+    const int parity = (int)(epoch & 1);
+    for (int r = 0; r < x.world; r++) {
+        pp.slot[r] = x.peer[r] + xch_rec_off(x, lane, parity, x.rank, rec);
+        pp.flag[r] = (unsigned long long*)(x.peer[r] + xch_flag_off(x, lane, parity, x.rank));
+    }
+    // broadcast over peer memory: one tiny kernel, payload then flag
+    k_exchange_send_t<PeerPtrs><<<1, 256, 0, (cudaStream_t)stream>>>(partial, (int)rec, pp, x.world, (unsigned long long)epoch);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+int bgls_final_exp_exchanged_dev(bgls_ctx* ctx, int curve, int lane, uint64_t epoch, void* d_out_gt, void* d_is_identity, void* stream) {
+    if (!ctx || !curve_ok(curve) || !d_out_gt || !ctx->xch.ready || lane < 0 || lane >= ctx->xch.lanes || epoch == 0)
+        return fail(ctx, BGLS_ERR_ARG, "bad argument / exchange not connected");
+    Exchange& x = ctx->xch;
+    SlotLock sl(ctx, (cudaStream_t)stream);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), rec = 12 * F;
+    const int parity = (int)(epoch & 1);
+    void* work;
+    int rc = dev_work(ctx, sl.s, mach_work_for(curve, x.world), &work);
+    if (rc) return rc;
+    k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)(x.local + xch_flag_off(x, lane, parity, 0)), x.world,
+                                                         (unsigned long long)epoch, x.d_err);
+    ctx->launches++;
+    return finish_bytes_dev(ctx, curve, x.local + xch_rec_off(x, lane, parity, 0, rec), x.world, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
 }
 int bgls_final_exp_product_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, void* d_out_gt,
                                void* d_is_identity, void* stream) {

@@ -129,6 +129,24 @@ int bgls_last_kernel_ms(bgls_ctx* ctx, float* ms_main, float* ms_finish);
 /* measured full-rate IMAD.WIDE.U32 throughput of this GPU (32x32+64 multiply-accumulates / s) */
 int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s);
 
+/* Peer-memory exchange of the per-GPU Miller products (multi-GPU sharding of one product; nothing in the
+ * reference corresponds to it).  One process per GPU: every rank creates a mailbox, the 64-byte CUDA IPC handles are
+ * exchanged out of band (e.g. one all-gather at start-up), every rank connects to every peer.  Then, per product and
+ * per `lane` (an independent sequence of products; `epoch` = 1, 2, 3, ... within a lane):
+ *   bgls_miller_product_exchange_dev  Miller loops + product of this rank's pairs, then ONE kernel stores the 12F-byte
+ *                                     partial into the mailbox of every rank over NVLink peer memory and raises the flags;
+ *   bgls_final_exp_exchanged_dev      waits (on the device, bounded) until all `world` partials of (lane, epoch) have
+ *                                     arrived, multiplies them and runs the final exponentiation -- on every rank.
+ * No host synchronisation and no collective library call is involved.  bgls_exchange_error reports a wait that timed
+ * out (a peer that never sent).  world <= 8. */
+int bgls_exchange_create(bgls_ctx* ctx, int world, int rank, int lanes, uint8_t* handle_out /* 64 bytes */);
+int bgls_exchange_connect(bgls_ctx* ctx, int peer_rank, const uint8_t* handle /* 64 bytes */);
+int bgls_exchange_error(bgls_ctx* ctx, int* err);
+int bgls_miller_product_exchange_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int lane,
+                                     uint64_t epoch, void* stream);
+int bgls_final_exp_exchanged_dev(bgls_ctx* ctx, int curve, int lane, uint64_t epoch, void* d_out_gt, void* d_is_identity,
+                                 void* stream);
+
 /* verifyAggSig -- bgls/bgls.go:94-119, the body of VerifyAggregateSignature (bgls.go:82-84, allow_duplicates = 0) and
  * KoskVerifyAggregateSignature / DistinctMsgVerifyAggregateSignature (allow_duplicates = 1; the caller prepends the
  * 0x01 byte / the public key to each message as bgls/blsKosk.go:100-106 and blsDistinctMessage.go:45-57 do).

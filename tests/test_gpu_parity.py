@@ -406,3 +406,41 @@ def test_verify_multi_signature_entry_point(ctx, cid, c):
         if n > 1:
             assert ctx.verify_multi_signature(cid, msg, keys[4 * c.nbytes:], n - 1, sig) is False
         assert ctx.verify_multi_signature(cid, msg, keys, n, c.marshal_g1(c.g1_add(c.unmarshal_g1(sig), c.g1))) is False
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_peer_memory_exchange_single_rank(cid, c):
+    """The peer-memory exchange path (bgls_exchange_*, bgls_miller_product_exchange_dev, bgls_final_exp_exchanged_dev)
+    with world = 1: mailbox, send kernel, flag wait and finish, several epochs on two lanes (both parities),
+    against PairingProduct on the same inputs."""
+    import torch
+
+    import bgls_b200
+    ctx2 = bgls_b200.Context(0)
+    try:
+        h = ctx2.exchange_create(1, 0, 2)
+        ctx2.exchange_connect(0, h)
+        rng = random.Random(12 + cid)
+        dev = torch.device("cuda", 0)
+        s = torch.cuda.current_stream().cuda_stream
+        F = c.nbytes
+        d_out = torch.zeros(12 * F, dtype=torch.uint8, device=dev)
+        d_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        for epoch in (1, 2, 3):
+            for lane, n in ((0, 5), (1, 40)):
+                if epoch == 2:
+                    g1, g2 = make_aggregate(cid, c, n - 1, rng)
+                else:
+                    g1, _ = rand_points(cid, c, 1, n, rng)
+                    g2, _ = rand_points(cid, c, 2, n, rng)
+                want, want_ok = ctx2.pairing_product(cid, g1, g2, n)
+                t1 = torch.frombuffer(bytearray(g1), dtype=torch.uint8).to(dev)
+                t2 = torch.frombuffer(bytearray(g2), dtype=torch.uint8).to(dev)
+                ctx2.miller_product_exchange_dev(cid, t1.data_ptr(), t2.data_ptr(), n, lane, epoch, s)
+                ctx2.final_exp_exchanged_dev(cid, lane, epoch, d_out.data_ptr(), d_flag.data_ptr(), s)
+                torch.cuda.synchronize()
+                assert bytes(d_out.cpu().numpy()) == want and bool(d_flag.item()) == want_ok
+                assert want_ok == (epoch == 2)
+        assert ctx2.exchange_error() == 0
+    finally:
+        ctx2.close()
