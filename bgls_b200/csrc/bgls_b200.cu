@@ -432,6 +432,7 @@ struct bgls_ctx {
     Exchange xch;
     Slot slots[NSLOT];
     std::atomic<unsigned> rr{0};
+    std::atomic<size_t> scratch_hint{0};
     std::mutex own_mu;
     bool thread_engine = false;  // BGLS_ENGINE=thread: thread-per-pair kernels only
     bool machine_only = false;   // BGLS_ENGINE=machine: dot-product machine at every size (no hybrid)
@@ -473,7 +474,11 @@ int ensure_scratch(bgls_ctx* ctx, Slot* sl, size_t bytes) {
     if (sl->scratch) CU(cudaFree(sl->scratch));
     sl->scratch = nullptr;
     sl->scratch_bytes = 0;
+    // all slots converge on the largest request seen by any of them: a slot grows at most once per new maximum
     size_t want = align_up(bytes + bytes / 4, 1 << 20);
+    size_t hint = ctx->scratch_hint.load();
+    while (hint < want && !ctx->scratch_hint.compare_exchange_weak(hint, want)) {}
+    if (hint > want) want = hint;
     CU(cudaMalloc(&sl->scratch, want));
     sl->scratch_bytes = want;
     return BGLS_OK;
