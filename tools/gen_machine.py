@@ -412,9 +412,10 @@ class Gen:
         ph.tasks = list(plain)
         for re, im, terms in triples:
             assert 0 < len(terms) <= half
-            ph.triples.append((re, im, [(a, b) for a, b in terms]))
-            ph.tasks += [(re, sum(([(a[0], b[0]), (a[1], b[1], -1)] for a, b in terms), [])),
-                         (im, sum(([(a[0], b[1]), (a[1], b[0])] for a, b in terms), []))]
+            terms = [(t[0], t[1], t[2] if len(t) > 2 else 1) for t in terms]   # (a, b, sign of the Fp2 product)
+            ph.triples.append((re, im, terms))
+            ph.tasks += [(re, sum(([(a[0], b[0], sg), (a[1], b[1], -sg)] for a, b, sg in terms), [])),
+                         (im, sum(([(a[0], b[1], sg), (a[1], b[0], sg)] for a, b, sg in terms), []))]
         self.emit(ph)
 
     def kdot_fits(self):
@@ -1139,6 +1140,15 @@ def build_miller_p(gen: Gen):
               (LCp[1], [(TH[0], Qx[1]), (TH[1], Qx[0]), (LA[0], Qy[1], -1), (LA[1], Qy[0], -1)])]
         return t + m2fp(LYp, LA, yP) + m2fp(LXp, TH, xP)
 
+    def add_dot2_phase(Qx, Qy):
+        """theta^2, lam^2 and lc = theta xQ - lam yQ as Karatsuba triples (2 terms) when the curve allows it: the 4-term
+        schoolbook form of lc would make the whole phase 4 terms deep."""
+        if KD:
+            gen.kdot([(Cc[0], Cc[1], [(TH, TH)]), (Dd[0], Dd[1], [(LA, LA)]), (LCp[0], LCp[1], [(TH, Qx), (LA, Qy, -1)])],
+                     m2fp(LYp, LA, yP) + m2fp(LXp, TH, xP))
+        else:
+            gen.dot(add_dot2(Qx, Qy))
+
     def add_lin2():
         return (line_tasks(lines["y"], pos["y"], [(LYp[0], 1)], [(LYp[1], 1)]) +
                 line_tasks(lines["x"], pos["x"], [(LXp[0], -1)], [(LXp[1], -1)]) +
@@ -1169,7 +1179,7 @@ def build_miller_p(gen: Gen):
         """FB = f^2, dbl line ready.  Ends with f in FA and (if `more`) the first DOT of the next doubling issued."""
         big_dot(sparse_triples(FA, FB), sparse_tasks(FA, FB), add_dot1(Qx, Qy))
         lin1(add_lin1())
-        gen.dot(add_dot2(Qx, Qy))
+        add_dot2_phase(Qx, Qy)
         lin1(add_lin2())
         big_dot(sparse_triples(FB, FA), sparse_tasks(FB, FA), add_dot3())
         lin1(add_lin3() + [gen.lin(FA[k][c], (FB[k][c], 1)) for k in range(6) for c in range(2)])
@@ -1216,7 +1226,7 @@ def build_miller_p(gen: Gen):
         def tail_add(Qx, Qy, src, dst):
             gen.dot(add_dot1(Qx, Qy))
             lin1(add_lin1())
-            gen.dot(add_dot2(Qx, Qy))
+            add_dot2_phase(Qx, Qy)
             lin1(add_lin2())
             big_dot(sparse_triples(dst, src), sparse_tasks(dst, src), add_dot3())
             lin1(add_lin3())
@@ -1226,7 +1236,7 @@ def build_miller_p(gen: Gen):
         # the last addition only contributes its line: the point update is not needed
         gen.dot(add_dot1(Q2x, nQ2y))
         lin1(add_lin1())
-        gen.dot(add_dot2(Q2x, nQ2y))
+        add_dot2_phase(Q2x, nQ2y)
         lin1(add_lin2())
         big_dot(sparse_triples(FA, FB), sparse_tasks(FA, FB), [])
     else:
@@ -1616,15 +1626,17 @@ def emit_tables(path):
                     # record: [0] dst, [1 + 2t], [2 + 2t] = a1 (bit 15: minus), a2, [1 + TM + 2t], [2 + TM + 2t] = b1, b2
                     Z = ref(gen.ZERO)
                     ntr, half = len(ph.triples), TM // 2
-                    hdr.append(3 | (half << 8) | (ntr << 16) | (getattr(ph, "K", 0) << 24))
                     lanes_ = []
                     for re, im, terms in ph.triples:
-                        lanes_.append((0xFFFF, [(a[1], None, b[1], None) for a, b in terms]))            # Q
-                        lanes_.append((ref(re), [(a[0], None, b[0], None) for a, b in terms]))            # P
-                        lanes_.append((ref(im), [(a[0], a[1], b[0], b[1]) for a, b in terms]))            # S
+                        lanes_.append((0xFFFF, [(a[1], None, b[1], None, sg) for a, b, sg in terms]))            # Q
+                        lanes_.append((ref(re), [(a[0], None, b[0], None, sg) for a, b, sg in terms]))            # P
+                        lanes_.append((ref(im), [(a[0], a[1], b[0], b[1], sg) for a, b, sg in terms]))            # S
                     for dst, terms in ph.tasks[:ph.nplain]:
                         lanes_.append((ref(dst), [(t[0], None, t[1], None, (t[2] if len(t) > 2 else 1)) for t in terms]))
                     assert len(lanes_) <= gen.lanes
+                    tk = max(len(terms) for _, terms in lanes_)     # terms actually present (<= half)
+                    assert 0 < tk <= half
+                    hdr.append(3 | (tk << 8) | (ntr << 16) | (getattr(ph, "K", 0) << 24))
                     for lane in range(gen.lanes):
                         r = [0xFFFF] + [Z] * (2 * TM) + [0]
                         if lane < len(lanes_):
