@@ -413,7 +413,7 @@ struct Slot {
     size_t scratch_bytes = 0;
     std::mutex mu;
 };
-constexpr int NSLOT = 8;
+constexpr int NSLOT = 16;
 
 // peer-memory exchange state (bgls_exchange_*): this rank's mailbox and the mapped mailboxes of the peers
 struct Exchange {
