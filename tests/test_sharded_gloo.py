@@ -27,6 +27,14 @@ class OracleEngine:
         from oracle import c_oracle as C
         return C.aggregate(curve, grp, pts, n, 1)
 
+    def pairing_check_batch(self, curve, g1, g2, offsets):
+        from oracle import c_oracle as C
+        from oracle import bgls_oracle as O
+        c = O.ALTBN128 if curve == 0 else O.BLS12_381
+        nb, one = c.nbytes, c.marshal_gt(c.fp12_one)
+        return [C.pairing_product(curve, g1[2 * nb * a:2 * nb * b], g2[4 * nb * a:4 * nb * b], b - a, 1, 0) == one
+                for a, b in zip(offsets[:-1], offsets[1:])]
+
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
@@ -51,6 +59,22 @@ def _worker(rank, world, port, q):
             rec = 4 * nb
             s = sharded.sharded_aggregate_points(OracleEngine(), cid, 2, pts[rec * lo:rec * hi], hi - lo)
             res[f"agg{cid}"] = s == C.aggregate(cid, 2, pts, 7, 1)
+            # batch of 5 ragged checks (sizes 3, 1, 0, 2, 4 pairs), checks 1 and 3 corrupted: dealt 2 + 3 over the ranks
+            G1, G2, offs, expect = [], [], [0], []
+            for b, m in enumerate((2, 0, None, 1, 3)):
+                if m is None:          # an empty product is the identity
+                    offs.append(offs[-1])
+                    expect.append(True)
+                    continue
+                a1, a2 = make_aggregate(cid, c, m, rng, nthreads=1)
+                if b in (1, 3):
+                    a1 = a1[:-2 * nb] + c.marshal_g1(c.g1)
+                G1.append(a1)
+                G2.append(a2)
+                offs.append(offs[-1] + m + 1)
+                expect.append(b not in (1, 3))
+            got = sharded.sharded_pairing_check_batch(OracleEngine(), cid, b"".join(G1), b"".join(G2), offs)
+            res[f"batch{cid}"] = got == expect
     finally:
         dist.destroy_process_group()
     q.put((rank, res))
@@ -70,6 +94,7 @@ def test_sharded_world2_gloo():
         for cid in (0, 1):
             assert res[f"pair{cid}"] == (True, True), (rank, cid, res)
             assert res[f"agg{cid}"], (rank, cid)
+            assert res[f"batch{cid}"], (rank, cid)
 
 
 def test_shard_bounds_cover():
