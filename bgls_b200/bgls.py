@@ -10,6 +10,7 @@ argument order and accept/reject behaviour follow the reference line by line:
     AggregateSignatures / Keys      bgls/bgls.go:123-131
     KoskSign / KoskVerify*          bgls/blsKosk.go:74-150 (incl. batch multi-signature and multiplicity)
     DistinctMsg*                    bgls/blsDistinctMessage.go:22-57
+    *WithHAE                        bgls/blsHAE.go:39-93 (hashed aggregation exponents: BLAKE2Xb on the host, ScalePoints on the GPU)
     VerifyAggregateSignatures       engine extension: many independent aggregate verifies in one batched launch
 
 The only computation done here is control flow; every pairing, point sum, scalar multiplication and
@@ -147,6 +148,53 @@ def DistinctMsgVerifyAggregateSignature(curve, aggsig, keys, msgs):
     if len(keys) != len(msgs):
         return False
     return verifyAggSig(curve, aggsig, keys, [k.MarshalUncompressed() + bytes(m) for k, m in zip(keys, msgs)], True)
+
+
+# ---- Hashed aggregation exponents (bgls/blsHAE.go)
+def hashPubKeysToExponents(pubkeys):
+    """bgls/blsHAE.go:81-93: the uncompressed marshal of every key goes into one BLAKE2Xb instance of 16 n output
+    bytes; t_i is the i-th 16-byte big-endian word."""
+    from .blake2x import blake2xb
+    n = len(pubkeys)
+    if n == 0:
+        return []
+    out = blake2xb(b"".join(pk.MarshalUncompressed() for pk in pubkeys), 16 * n)
+    return [int.from_bytes(out[16 * i:16 * i + 16], "big") for i in range(n)]
+
+
+def AggregateSignaturesWithHAE(sigs, pubkeys):
+    """bgls/blsHAE.go:39-46: nil when the counts differ."""
+    from .curves import ScalePoints
+    if len(pubkeys) != len(sigs):
+        return None
+    return AggregatePoints(ScalePoints(sigs, hashPubKeysToExponents(pubkeys)))
+
+
+def VerifyAggregateSignatureWithHAE(curve, aggsig, pubkeys, msgs):
+    """bgls/blsHAE.go:49-53: the keys scaled by their exponents (one ScalePoints launch), then verifyAggSig with
+    duplicates allowed."""
+    from .curves import ScalePoints
+    return verifyAggSig(curve, aggsig, ScalePoints(pubkeys, hashPubKeysToExponents(pubkeys)), msgs, True)
+
+
+def getAggregatePubKey(curve, pubkeys):
+    """bgls/blsHAE.go:75-78"""
+    from .curves import ScalePoints
+    return AggregatePoints(ScalePoints(pubkeys, hashPubKeysToExponents(pubkeys)))
+
+
+def VerifyMultiSignatureWithHAE(curve, aggsig, pubkeys, msg):
+    """bgls/blsHAE.go:56-58"""
+    return VerifySingleSignature(curve, aggsig, getAggregatePubKey(curve, pubkeys), msg)
+
+
+def VerifyBatchMultiSignatureWithHAE(curve, aggsigs, aggpubkeys, msgs, allowDups):
+    """bgls/blsHAE.go:62-72.  With allowDups the reference draws random factors and calls ScalePoints(aggsigs, t) but
+    discards the result (blsHAE.go:68), so the factors never enter the check: the same happens here."""
+    from .curves import ScalePoints
+    if allowDups:
+        ScalePoints(aggsigs, [secrets.randbelow(curve.GetG1Order()) for _ in aggsigs])
+    return verifyAggSig(curve, AggregateSignatures(aggsigs), aggpubkeys, msgs, True)
 
 
 def VerifyAggregateSignatures(curve, items):

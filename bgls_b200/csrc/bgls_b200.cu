@@ -411,8 +411,11 @@ struct Slot {
     bool owned = false;
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    uint8_t* hres = nullptr;         // pinned host buffer for the small results (GT bytes + verdict): the device-to-host
+                                     // copy of a call never goes through the driver's pageable staging path
     std::mutex mu;
 };
+constexpr size_t HRES_BYTES = 1024;
 constexpr int NSLOT = 16;
 
 // peer-memory exchange state (bgls_exchange_*): this rank's mailbox and the mapped mailboxes of the peers
@@ -910,7 +913,8 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
         ok = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
              cudaStreamCreateWithFlags(&sl.aux, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+             cudaHostAlloc((void**)&sl.hres, HRES_BYTES, cudaHostAllocDefault) == cudaSuccess;
     }
     if (!ok) {
         for (auto& sl : ctx->slots) {
@@ -918,6 +922,7 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
             if (sl.aux) cudaStreamDestroy(sl.aux);
             if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
             if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+            if (sl.hres) cudaFreeHost(sl.hres);
         }
         delete ctx;
         return BGLS_ERR_CUDA;
@@ -945,6 +950,7 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& sl : ctx->slots) {
         if (sl.scratch) cudaFree(sl.scratch);
+        if (sl.hres) cudaFreeHost(sl.hres);
         if (sl.stream) cudaStreamDestroy(sl.stream);
         if (sl.aux) cudaStreamDestroy(sl.aux);
         if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
@@ -1028,7 +1034,7 @@ static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8
     }
     rc = pairing_dev(ctx, curve, d1, d2, n, do_final, dout, dflag, work, sl.s->stream);
     if (rc) return rc;
-    uint8_t hbuf[12 * 48 + 16];
+    uint8_t* hbuf = sl.s->hres;
     CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, sl.s->stream));
     CU(cudaStreamSynchronize(sl.s->stream));
     memcpy(out, hbuf, 12 * F);
@@ -1056,7 +1062,7 @@ int bgls_final_exp_product(bgls_ctx* ctx, int curve, const uint8_t* partials, si
     if (k) CU(cudaMemcpyAsync(din, partials, k * 12 * F, cudaMemcpyHostToDevice, sl.s->stream));
     rc = finish_bytes_dev(ctx, curve, din, k, 1, dout, dflag, dout + bo, sl.s->stream);
     if (rc) return rc;
-    uint8_t hbuf[12 * 48 + 16];
+    uint8_t* hbuf = sl.s->hres;
     CU(cudaMemcpyAsync(hbuf, dout, 12 * F + 4, cudaMemcpyDeviceToHost, sl.s->stream));
     CU(cudaStreamSynchronize(sl.s->stream));
     memcpy(out_gt, hbuf, 12 * F);
@@ -1282,10 +1288,9 @@ int bgls_verify_aggregate_signature(bgls_ctx* ctx, int curve, const uint8_t* msg
     if (rc) return rc;
     rc = pairing_dev(ctx, curve, d1, d2, np, 1, dout, dflag, work, s);    // PairingProduct(pts1, pts2), bgls.go:114
     if (rc) return rc;
-    int flag = 0;
-    CU(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(sl.s->hres, dflag, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));   // also keeps `rel` and `tail` alive until the copies are done
-    *ok = flag;                     // aggPt.Equals(GetGTIdentity()), bgls.go:115-118
+    memcpy(ok, sl.s->hres, 4);      // aggPt.Equals(GetGTIdentity()), bgls.go:115-118
     return BGLS_OK;
 }
 int bgls_verify_multi_signature(bgls_ctx* ctx, int curve, const uint8_t* msg, size_t msg_len, const uint8_t* keys, size_t n,
@@ -1327,10 +1332,9 @@ int bgls_verify_multi_signature(bgls_ctx* ctx, int curve, const uint8_t* msg, si
     CU(cudaStreamWaitEvent(s, sl.s->ev_join, 0));
     rc = pairing_dev(ctx, curve, d1, d2, 2, 1, dout, dflag, work, s);
     if (rc) return rc;
-    int flag = 0;
-    CU(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(sl.s->hres, dflag, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    *ok = flag;
+    memcpy(ok, sl.s->hres, 4);
     return BGLS_OK;
 }
 int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, const uint64_t* offsets,
