@@ -1081,8 +1081,9 @@ int bgls_gt_mul(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* b, ui
     CU(cudaMemcpyAsync(din + 12 * F, b, 12 * F, cudaMemcpyHostToDevice, sl.s->stream));
     rc = finish_bytes_dev(ctx, curve, din, 2, 0, dout, nullptr, dout + bo, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_gt, dout, 12 * F, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaMemcpyAsync(sl.s->hres, dout, 12 * F, cudaMemcpyDeviceToHost, sl.s->stream));
     CU(cudaStreamSynchronize(sl.s->stream));
+    memcpy(out_gt, sl.s->hres, 12 * F);
     return BGLS_OK;
 }
 int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out) {
@@ -1097,8 +1098,9 @@ int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pt
     CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, sl.s->stream));
     rc = aggregate_dev(ctx, curve, group, din, n, dout, work, sl.s->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaMemcpyAsync(sl.s->hres, dout, rec, cudaMemcpyDeviceToHost, sl.s->stream));
     CU(cudaStreamSynchronize(sl.s->stream));
+    memcpy(out, sl.s->hres, rec);
     return BGLS_OK;
 }
 int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, const uint8_t* scalars, size_t n, uint8_t* out) {
