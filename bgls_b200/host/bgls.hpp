@@ -13,6 +13,7 @@
 // The cgo binding a Go maintainer adds instead of this file is in INTEGRATION.md.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -516,6 +517,111 @@ inline bool KoskVerifyMultiSignatureWithMultiplicity(const CurveSystem& curve, c
     std::vector<Int> f(multiplicity.begin(), multiplicity.end());
     auto scaled = curves::ScalePoints(keys, f);
     return scaled.second && KoskVerifyMultiSignature(curve, aggsig, scaled.first, msg);
+}
+
+// ---- blsHAE.go: hashed aggregation exponents.  The hash G^n -> R^n is BLAKE2Xb (golang.org/x/crypto/blake2b.NewXOF),
+// restated from the BLAKE2 / BLAKE2X specifications; host glue only (16 bytes per key), the scalings run on the GPU.
+namespace blake2 {
+inline uint64_t rotr(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+inline void compress(uint64_t h[8], const uint8_t block[128], uint64_t t, bool last) {
+    static const uint64_t IV[8] = {0x6A09E667F3BCC908ull, 0xBB67AE8584CAA73Bull, 0x3C6EF372FE94F82Bull, 0xA54FF53A5F1D36F1ull,
+                                   0x510E527FADE682D1ull, 0x9B05688C2B3E6C1Full, 0x1F83D9ABFB41BD6Bull, 0x5BE0CD19137E2179ull};
+    static const uint8_t S[12][16] = {
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+        {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+        {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+        {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+        {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+    uint64_t m[16], v[16];
+    for (int i = 0; i < 16; i++) {
+        m[i] = 0;
+        for (int b = 7; b >= 0; b--) m[i] = (m[i] << 8) | block[8 * i + b];
+    }
+    for (int i = 0; i < 8; i++) { v[i] = h[i]; v[8 + i] = IV[i]; }
+    v[12] ^= t;
+    if (last) v[14] = ~v[14];
+    auto G = [&](int a, int b, int c, int d, uint64_t x, uint64_t y) {
+        v[a] = v[a] + v[b] + x; v[d] = rotr(v[d] ^ v[a], 32);
+        v[c] = v[c] + v[d];     v[b] = rotr(v[b] ^ v[c], 24);
+        v[a] = v[a] + v[b] + y; v[d] = rotr(v[d] ^ v[a], 16);
+        v[c] = v[c] + v[d];     v[b] = rotr(v[b] ^ v[c], 63);
+    };
+    for (int r = 0; r < 12; r++) {
+        const uint8_t* s = S[r];
+        G(0, 4, 8, 12, m[s[0]], m[s[1]]);   G(1, 5, 9, 13, m[s[2]], m[s[3]]);
+        G(2, 6, 10, 14, m[s[4]], m[s[5]]);  G(3, 7, 11, 15, m[s[6]], m[s[7]]);
+        G(0, 5, 10, 15, m[s[8]], m[s[9]]);  G(1, 6, 11, 12, m[s[10]], m[s[11]]);
+        G(2, 7, 8, 13, m[s[12]], m[s[13]]); G(3, 4, 9, 14, m[s[14]], m[s[15]]);
+    }
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+// unkeyed BLAKE2b of `data` under an explicit parameter block (first 18 bytes given, the rest zero): 64-byte state
+inline Bytes hash(const Bytes& data, uint8_t digest_len, uint8_t fanout, uint8_t depth, uint32_t leaf_len, uint32_t node_offset,
+                  uint32_t xof_len, uint8_t node_depth, uint8_t inner_len) {
+    static const uint64_t IV[8] = {0x6A09E667F3BCC908ull, 0xBB67AE8584CAA73Bull, 0x3C6EF372FE94F82Bull, 0xA54FF53A5F1D36F1ull,
+                                   0x510E527FADE682D1ull, 0x9B05688C2B3E6C1Full, 0x1F83D9ABFB41BD6Bull, 0x5BE0CD19137E2179ull};
+    uint8_t p[64] = {0};
+    p[0] = digest_len; p[2] = fanout; p[3] = depth;
+    for (int i = 0; i < 4; i++) { p[4 + i] = (uint8_t)(leaf_len >> (8 * i)); p[8 + i] = (uint8_t)(node_offset >> (8 * i)); p[12 + i] = (uint8_t)(xof_len >> (8 * i)); }
+    p[16] = node_depth; p[17] = inner_len;
+    uint64_t h[8];
+    for (int i = 0; i < 8; i++) {
+        uint64_t w = 0;
+        for (int b = 7; b >= 0; b--) w = (w << 8) | p[8 * i + b];
+        h[i] = IV[i] ^ w;
+    }
+    const size_t nblk = data.empty() ? 1 : (data.size() + 127) / 128;
+    for (size_t i = 0; i < nblk; i++) {
+        uint8_t blk[128] = {0};
+        const size_t off = 128 * i, len = data.size() > off ? std::min<size_t>(128, data.size() - off) : 0;
+        if (len) std::memcpy(blk, data.data() + off, len);
+        const bool last = i == nblk - 1;
+        compress(h, blk, last ? data.size() : 128 * (i + 1), last);
+    }
+    Bytes out(64);
+    for (int i = 0; i < 8; i++)
+        for (int b = 0; b < 8; b++) out[8 * i + b] = (uint8_t)(h[i] >> (8 * b));
+    return out;
+}
+// out_len bytes of BLAKE2Xb(data): H0 = BLAKE2b-64 with the XOF length in the parameter block, block i = BLAKE2b(H0) with
+// fanout 0, depth 0, leaf length 64, node offset i, inner length 64
+inline Bytes xof(const Bytes& data, uint32_t out_len) {
+    Bytes h0 = hash(data, 64, 1, 1, 0, 0, out_len, 0, 0), out;
+    for (uint32_t i = 0; 64 * i < out_len; i++) {
+        const uint32_t j = std::min<uint32_t>(64, out_len - 64 * i);
+        Bytes b = hash(h0, (uint8_t)j, 0, 0, 64, i, out_len, 0, 64);
+        out.insert(out.end(), b.begin(), b.begin() + j);
+    }
+    return out;
+}
+}  // namespace blake2
+
+inline std::vector<Int> hashPubKeysToExponents(const std::vector<Point>& pubkeys) {  // blsHAE.go:81-93
+    std::vector<Int> t;
+    if (pubkeys.empty()) return t;
+    Bytes all;
+    for (auto& pk : pubkeys) {
+        Bytes b = pk.MarshalUncompressed();
+        all.insert(all.end(), b.begin(), b.end());
+    }
+    Bytes x = blake2::xof(all, (uint32_t)(16 * pubkeys.size()));
+    for (size_t i = 0; i < pubkeys.size(); i++) t.push_back(Int::FromBytes(x.data() + 16 * i, 16));
+    return t;
+}
+inline Point AggregateSignaturesWithHAE(const std::vector<Point>& sigs, const std::vector<Point>& pubkeys) {  // blsHAE.go:39-46
+    if (pubkeys.size() != sigs.size()) return Point();
+    return curves::AggregatePoints(curves::ScalePoints(sigs, hashPubKeysToExponents(pubkeys)).first);
+}
+inline bool VerifyAggregateSignatureWithHAE(const CurveSystem& curve, const Point& aggsig, const std::vector<Point>& pubkeys,
+                                            const std::vector<Bytes>& msgs) {  // blsHAE.go:49-53
+    return verifyAggSig(curve, aggsig, curves::ScalePoints(pubkeys, hashPubKeysToExponents(pubkeys)).first, msgs, true);
+}
+inline Point getAggregatePubKey(const CurveSystem&, const std::vector<Point>& pubkeys) {  // blsHAE.go:75-78
+    return curves::AggregatePoints(curves::ScalePoints(pubkeys, hashPubKeysToExponents(pubkeys)).first);
+}
+inline bool VerifyMultiSignatureWithHAE(const CurveSystem& curve, const Point& aggsig, const std::vector<Point>& pubkeys, const Bytes& msg) {
+    return VerifySingleSignature(curve, aggsig, getAggregatePubKey(curve, pubkeys), msg);  // blsHAE.go:56-58
 }
 
 }  // namespace bgls

@@ -127,6 +127,36 @@ static void TestKosk(const CurveSystem& curve, uint64_t& seed) {  // blsKosk_tes
     CHECK(!KoskVerifyBatchMultiSignature(curve, {agg, AggregateSignatures(sigs2)}, {keys, fewer}, {msg, msg2}), "batch multi-signature accepted with a key missing");
 }
 
+static void TestHAE(const CurveSystem& curve, uint64_t& seed) {  // blsHAE_test.go:14-83
+    const int N = 5;
+    std::vector<Bytes> msgs;
+    std::vector<Point> sigs, pubkeys;
+    for (int i = 0; i < N; i++) {
+        msgs.push_back(rand_bytes(32, seed));
+        auto kp = KeyGen(curve);
+        sigs.push_back(Sign(curve, kp.first, msgs[i]));
+        pubkeys.push_back(kp.second);
+    }
+    Point agg = AggregateSignaturesWithHAE(sigs, pubkeys);
+    CHECK(VerifyAggregateSignatureWithHAE(curve, agg, pubkeys, msgs), "HAE aggregate verification failed");
+    std::vector<Point> fewer(pubkeys.begin(), pubkeys.end() - 1);
+    CHECK(!VerifyAggregateSignatureWithHAE(curve, agg, fewer, msgs), "HAE succeeding without enough pubkeys");
+    CHECK(AggregateSignaturesWithHAE(sigs, fewer).nil(), "HAE aggregation with differing counts must give nil");
+    CHECK(!VerifyAggregateSignatureWithHAE(curve, AggregateSignatures(sigs), pubkeys, msgs), "plain aggregate accepted as HAE aggregate");
+    Bytes msg = rand_bytes(32, seed);
+    std::vector<Point> msigs, signers;
+    for (int j = 0; j < 8; j++) {
+        auto kp = KeyGen(curve);
+        msigs.push_back(Sign(curve, kp.first, msg));
+        signers.push_back(kp.second);
+    }
+    Point magg = AggregateSignaturesWithHAE(msigs, signers);
+    CHECK(VerifyMultiSignatureWithHAE(curve, magg, signers, msg), "HAE multi-signature verification failed");
+    CHECK(!VerifyMultiSignatureWithHAE(curve, magg, signers, rand_bytes(32, seed)), "HAE multi-signature accepted on another message");
+    signers[0] = KeyGen(curve).second;
+    CHECK(!VerifyMultiSignatureWithHAE(curve, magg, signers, msg), "HAE multi-signature accepted with a wrong signer");
+}
+
 static void TestCurveLayer(const CurveSystem& curve, const CurveSystem& other, uint64_t& seed) {
     // curve_test.go:143-165: PairingProduct == product of Pair
     const int N = 5;
@@ -192,6 +222,12 @@ static void Dump(const CurveSystem& curve) {
     std::vector<Point> hs = curve.HashToG1Many(msgs);
     std::printf("%s.product %s\n", n.c_str(), hex(curve.PairingProduct(hs, keys).first.Marshal()).c_str());
     std::printf("%s.pair %s\n", n.c_str(), hex(curve.Pair(hs[0], keys[0]).first.Marshal()).c_str());
+    {
+        Bytes t;
+        for (auto& e : hashPubKeysToExponents(keys)) t.insert(t.end(), e.mag.begin() + 16, e.mag.end());
+        std::printf("%s.hae_exponents %s\n", n.c_str(), hex(t).c_str());
+        std::printf("%s.hae_aggsig %s\n", n.c_str(), hex(AggregateSignaturesWithHAE(sigs, keys).MarshalUncompressed()).c_str());
+    }
     std::printf("%s.verify %d\n", n.c_str(), (int)VerifyAggregateSignature(curve, agg, keys, msgs));
     msgs[1][0] ^= 1;
     std::printf("%s.verify_bad %d\n", n.c_str(), (int)VerifyAggregateSignature(curve, agg, keys, msgs));
@@ -199,6 +235,14 @@ static void Dump(const CurveSystem& curve) {
 
 int main(int argc, char** argv) {
     try {
+        if (argc > 1 && std::string(argv[1]) == "--blake2x") {   // host-only: no GPU needed
+            for (int n : {0, 1, 64, 128, 129, 300}) {
+                Bytes d(n);
+                for (int k = 0; k < n; k++) d[k] = (uint8_t)(7 * k + n);
+                for (uint32_t len : {16u, 64u, 80u, 200u}) std::printf("%d %u %s\n", n, len, hex(bgls::blake2::xof(d, len)).c_str());
+            }
+            return 0;
+        }
         if (argc > 1 && std::string(argv[1]) == "--dump") {
             Dump(Altbn128());
             Dump(Bls12());
@@ -210,6 +254,7 @@ int main(int argc, char** argv) {
             TestSingleSigner(*cs[i], seed);
             TestAggregation(*cs[i], seed);
             TestKosk(*cs[i], seed);
+            TestHAE(*cs[i], seed);
             TestCurveLayer(*cs[i], *cs[1 - i], seed);
         }
     } catch (const std::exception& e) {

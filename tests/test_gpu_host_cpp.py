@@ -36,6 +36,19 @@ def test_host_cpp_builds_and_refuses_without_gpu():
     assert r.returncode == 2 and "no CUDA device" in r.stderr
 
 
+def test_host_cpp_blake2xb_matches_python():
+    """CPU: the C++ BLAKE2Xb of the hashed aggregation exponents against bgls_b200/blake2x.py (itself pinned on hashlib)."""
+    from bgls_b200.blake2x import blake2xb
+    r = subprocess.run([build_host_test(), "--blake2x"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 24
+    for line in lines:
+        n, length, hx = line.split()
+        n, length = int(n), int(length)
+        assert hx == blake2xb(bytes((7 * k + n) & 0xFF for k in range(n)), length).hex(), (n, length)
+
+
 @pytest.mark.gpu
 def test_reference_tests_in_cpp():
     r = subprocess.run([build_host_test()], capture_output=True, text=True, timeout=600)
@@ -64,4 +77,10 @@ def test_transcript_matches_oracle():
         assert got[f"{name}.aggkey"] == C.aggregate(cid, 2, b"".join(pks), n, 1).hex()
         assert got[f"{name}.product"] == C.pairing_product(cid, b"".join(hs), b"".join(pks), n, 1, 0).hex()
         assert got[f"{name}.pair"] == C.pairing_product(cid, hs[0], pks[0], 1, 1, 0).hex()
+        # hashed aggregation exponents: the C++ BLAKE2Xb against the Python one, the scaled sum against the oracle
+        from bgls_b200.blake2x import blake2xb
+        ex = blake2xb(b"".join(pks), 16 * n)
+        assert got[f"{name}.hae_exponents"] == ex.hex()
+        scaled = C.scale_points(cid, 1, b"".join(sigs), b"".join(bytes(16) + ex[16 * i:16 * i + 16] for i in range(n)), n, 1)
+        assert got[f"{name}.hae_aggsig"] == C.aggregate(cid, 1, scaled, n, 1).hex()
         assert got[f"{name}.verify"] == "1" and got[f"{name}.verify_bad"] == "0"
