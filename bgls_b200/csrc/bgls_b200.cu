@@ -416,7 +416,7 @@ struct Slot {
     std::mutex mu;
 };
 constexpr size_t HRES_BYTES = 1024;
-constexpr int NSLOT = 16;
+constexpr int NSLOT = 24;
 
 // peer-memory exchange state (bgls_exchange_*): this rank's mailbox and the mapped mailboxes of the peers
 struct Exchange {

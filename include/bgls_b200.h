@@ -25,10 +25,10 @@
  *     (as void*), enqueue the work and return without synchronising.
  *   - a context is bound to one CUDA device and is safe to share between threads / goroutines (the
  *     reference calls Pair / PairingProduct from many goroutines, curves/curve.go:132-134).  It owns
- *     16 execution slots (stream + device scratch each): concurrent host-buffer calls run on different
+ *     24 execution slots (stream + device scratch each): concurrent host-buffer calls run on different
  *     slots and overlap on the GPU -- the single-warp final exponentiation of one product beside the
  *     Miller loops of the next.  `_dev` calls are keyed by the caller's stream: work enqueued on
- *     different streams uses different scratch; more than 16 streams in flight are serialised.
+ *     different streams uses different scratch; more than 24 streams in flight are serialised.
  *     bgls_last_error() returns the text of the most recent failing call on the context.
  */
 #ifndef BGLS_B200_H

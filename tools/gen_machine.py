@@ -1410,20 +1410,55 @@ def build_final_exp(gen: Gen):
     def conj(a):
         d = alloc(); gen.f12_conj(d, a); return d
 
+    def wnaf3(e):
+        """Signed digits of e in {0, +-1, +-3} (width-3 non-adjacent form), least significant first."""
+        out = []
+        while e:
+            if e & 1:
+                d = e % 8
+                if d > 4:
+                    d -= 8
+                e -= d
+            else:
+                d = 0
+            out.append(d)
+            e >>= 1
+        return out
+
     def cyc_pow(base, e):
-        """base^e by square-and-multiply with cyclotomic squarings (fresh register returned)."""
-        bder = gen.f12_derived(base, "PDER")
-        cur_ = base
-        for ch in bin(e)[3:]:
+        """base^e for base in the cyclotomic subgroup (fresh register returned): cyclotomic squarings and a signed
+        width-3 window -- the table is base^{+-1}, base^{+-3}, the inverses being conjugates -- so a 63-bit exponent
+        costs ~16 multiplications instead of one per set bit."""
+        digs = wnaf3(e)
+        assert sum(d << i for i, d in enumerate(digs)) == e
+        if bin(e).count("1") - sum(1 for d in digs if d) < 4:
+            digs = [int(ch) for ch in bin(e)[:1:-1]]     # sparse exponent (bls12-381 x): the table would cost more than it saves
+        tbl, owned = {1: base}, []
+        if any(abs(d) == 3 for d in digs):
+            sq = csq(base)
+            tbl[3] = mul(sq, base)
+            free(sq)
+            owned.append(tbl[3])
+        for k in (1, 3):
+            if k in tbl and any(d == -k for d in digs):
+                tbl[-k] = conj(tbl[k])
+                owned.append(tbl[-k])
+        der = {k: gen.f12_derived(v, "PDER%s%d" % ("m" if k < 0 else "p", abs(k))) for k, v in sorted(tbl.items())}
+        top = len(digs) - 1
+        cur_, fresh = tbl[digs[top]], False      # the leading digit of a width-3 NAF of a positive number is positive
+        assert digs[top] > 0
+        for i in range(top - 1, -1, -1):
             nx = csq(cur_)
-            if cur_ is not base:
+            if fresh:
                 free(cur_)
-            cur_ = nx
-            if ch == "1":
+            cur_, fresh = nx, True
+            if digs[i]:
                 nx = alloc()
-                gen.f12_mul(nx, cur_, base, bder=bder)
+                gen.f12_mul(nx, cur_, tbl[digs[i]], bder=der[digs[i]])
                 free(cur_)
                 cur_ = nx
+        assert fresh, "exponents of the final exponentiation have more than one digit"
+        free(*owned)
         return cur_
 
     if cfg.name == "BN254":
