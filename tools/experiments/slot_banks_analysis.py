@@ -1,3 +1,5 @@
+"""Experiment: shared-memory wavefronts per warp-wide slot access of every generated program under the current slot
+numbering (1.0 = conflict free); see slot_banks_anneal.py.      python tools/experiments/slot_banks_analysis.py"""
 import sys, collections, time
 sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), '..'))
 import gen_machine as G

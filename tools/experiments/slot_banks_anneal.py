@@ -1,7 +1,15 @@
-import os, sys
+"""Experiment (not part of the product, result in DESIGN.md section 5): renumber the slots of each slot file by seeded
+annealing so that the lanes of a warp-wide operand fetch hit different shared-memory banks.  Removes the bank conflicts
+(1.49 -> 1.02 wavefronts per access with all slots free) but does not change any kernel time on B200, so the generator
+keeps its natural numbering.      python tools/experiments/slot_banks_anneal.py"""
+import collections
+import os
+import random
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import sys, collections, random, time
-sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), '..'))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import gen_machine as G
 from slot_banks_analysis import instrs_of_phase
 
