@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -22,6 +23,7 @@
 #include "../../include/bgls_b200.h"
 #include "pairing.cuh"
 #include "machine_kernels.cuh"
+#include "slotvm.cuh"
 #include "hash.cuh"
 #include "codec.cuh"
 
@@ -407,6 +409,8 @@ struct Slot {
     cudaStream_t stream = nullptr;   // the slot's own stream (host-buffer calls)
     cudaStream_t aux = nullptr;      // second stream for independent work inside one call (fork / join events below)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_done = nullptr;   // recorded on the caller's stream at the end of every device-resident call using this slot
+    std::atomic<long long> last_use_us{0};   // time of the last pairing call that used this slot (load estimate)
     cudaStream_t owner = nullptr;    // caller stream this slot's scratch is currently ordered on (device-resident calls)
     bool owned = false;
     void* scratch = nullptr;
@@ -430,8 +434,18 @@ struct Exchange {
 };
 constexpr size_t XREC = 640;                  // 12 * 48 bytes rounded up to a multiple of 128
 
+// device copies of the slot engine's tables of one curve (slotvm.cuh), G = 4 lanes per pair
+struct SlotEngDev {
+    SvTables tb{};
+    void* blob = nullptr;
+};
+enum { ENGINE_AUTO = 0, ENGINE_MACHINE, ENGINE_THREAD, ENGINE_SLOT };
+
 struct bgls_ctx {
     MachDev mach[2];
+    SlotEngDev sloteng[2];
+    int engine = ENGINE_AUTO;        // BGLS_ENGINE=auto|machine|thread|slot
+    std::atomic<int> host_calls{0};  // host-buffer pairing calls currently inside the library
     Exchange xch;
     Slot slots[NSLOT];
     std::atomic<unsigned> rr{0};
@@ -473,7 +487,9 @@ size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 int ensure_scratch(bgls_ctx* ctx, Slot* sl, size_t bytes) {
     if (bytes <= sl->scratch_bytes) return BGLS_OK;
-    // the old buffer may still be in use by work enqueued earlier (cudaFree waits for the device)
+    // GROWTH SYNCHRONISES (documented in include/bgls_b200.h): the old buffer may still be in use by work enqueued earlier,
+    // so the first call of a given size on a slot waits for the device; steady-state calls never get here.
+    // Not legal inside a stream capture: warm the context up with one call of the largest size before capturing.
     CU(cudaDeviceSynchronize());
     if (sl->scratch) CU(cudaFree(sl->scratch));
     sl->scratch = nullptr;
@@ -799,12 +815,81 @@ int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8
     return BGLS_OK;
 }
 
+// ---- slot engine (slotvm.cuh): Miller loops on saturated limbs, G lanes per pair
+using SlotBN = svt::BN254_G4;
+using SlotBLS = svt::BLS381_G4;
+constexpr int SLOT_WPB = 1;   // one warp per block: 8 pairs, ~20 / 30 KB of shared memory -> 10 / 7 resident warps per SM
+template <class C, class T> int upload_slot(bgls_ctx* ctx, SlotEngDev& d) {
+    const size_t b0 = align_up((size_t)T::NWORDS * 4), b1 = align_up((size_t)(T::NPROG + 1) * 4), b2 = align_up((size_t)T::SEQ_LEN),
+                 b3 = align_up((size_t)T::NCONST * 2 * C::N * 4);
+    CU(cudaMalloc(&d.blob, b0 + b1 + b2 + b3));
+    char* p = (char*)d.blob;
+    CU(cudaMemcpy(p, T::code(), (size_t)T::NWORDS * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p + b0, T::offsets(), (size_t)(T::NPROG + 1) * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p + b0 + b1, T::sequence(), (size_t)T::SEQ_LEN, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p + b0 + b1 + b2, T::consts(), (size_t)T::NCONST * 2 * C::N * 4, cudaMemcpyHostToDevice));
+    d.tb.code = (const uint32_t*)p;
+    d.tb.offs = (const uint32_t*)(p + b0);
+    d.tb.seq = (const uint8_t*)(p + b0 + b1);
+    d.tb.consts = (const uint32_t*)(p + b0 + b1 + b2);
+    constexpr int NPB = SLOT_WPB * 32 / T::G;
+    CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem_bytes<C, T, NPB>()));
+    return BGLS_OK;
+}
+size_t slot_blocks(size_t n) { return (n + (SLOT_WPB * 32 / 4) - 1) / (SLOT_WPB * 32 / 4); }
+// Miller loops of n pairs -> slot_blocks(n) raw partial products as GT wire records
+int slot_miller(bgls_ctx* ctx, int curve, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, uint8_t* d_partials, cudaStream_t s) {
+    const unsigned nb = (unsigned)slot_blocks(n);
+    if (curve == BGLS_ALTBN128) {
+        constexpr int NPB = SLOT_WPB * 32 / SlotBN::G;
+        k_slot_miller<BN254, SlotBN, SLOT_WPB><<<nb, SLOT_WPB * 32, sv_smem_bytes<BN254, SlotBN, NPB>(), s>>>(ctx->sloteng[0].tb, d_g1, d_g2, n, d_partials);
+    } else {
+        constexpr int NPB = SLOT_WPB * 32 / SlotBLS::G;
+        k_slot_miller<BLS381, SlotBLS, SLOT_WPB><<<nb, SLOT_WPB * 32, sv_smem_bytes<BLS381, SlotBLS, NPB>(), s>>>(ctx->sloteng[1].tb, d_g1, d_g2, n, d_partials);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+// load estimate: pairing calls inside the library (host-buffer entry points) or recently enqueued (device-resident ones)
+long long now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+int busy_estimate(bgls_ctx* ctx) {
+    const long long t = now_us();
+    int recent = 0;
+    for (auto& sl : ctx->slots) recent += (t - sl.last_use_us.load(std::memory_order_relaxed)) < 3000 ? 1 : 0;
+    const int hc = ctx->host_calls.load(std::memory_order_relaxed);
+    return hc > recent ? hc : recent;
+}
+constexpr size_t SLOT_MIN_PAIRS = 32;     // below this a product is a handful of warps either way: the machine's one warp per pairing is faster
+constexpr size_t SLOT_BIG_PAIRS = 2048;   // from here one product alone fills the GPU with the slot engine
+constexpr int SLOT_MIN_BUSY = 3;          // products in flight from which throughput matters more than the latency of one
+bool use_slot_engine(bgls_ctx* ctx, size_t n) {
+    if (ctx->engine == ENGINE_SLOT) return n > 0;
+    if (ctx->engine != ENGINE_AUTO || n < SLOT_MIN_PAIRS) return false;
+    return n >= SLOT_BIG_PAIRS || busy_estimate(ctx) >= SLOT_MIN_BUSY;
+}
+
 size_t mach_work_for(int curve, size_t n) {
     return curve == BGLS_ALTBN128 ? mach_work_bytes<mtab::BN254_M>(n) : mach_work_bytes<mtab::BLS381_M>(n);
 }
 int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
                 void* d_flag, void* work, cudaStream_t s) {
     if (ctx->thread_engine) return pairing_dev_thread(ctx, curve, d_g1, d_g2, n, do_final, d_out, d_flag, work, s);
+    if (use_slot_engine(ctx, n)) {
+        // throughput regime: Miller loops on the slot engine (saturated limbs, 4 lanes per pair, one raw partial product per
+        // block of 8 pairs), then the machine multiplies the partials and runs the one final exponentiation.
+        // Layout of `work`: [partial wire records | machine scratch]
+        const size_t nb = slot_blocks(n);
+        uint8_t* parts = (uint8_t*)work;
+        uint8_t* mw = parts + align_up(nb * 12 * fp_bytes(curve));
+        if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
+        int rc = slot_miller(ctx, curve, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, parts, s);
+        if (rc) return rc;
+        if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
+        rc = finish_bytes_dev(ctx, curve, parts, nb, do_final, d_out, d_flag, mw, s);
+        if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
+        return rc;
+    }
     if (n >= MHYBRID && !ctx->machine_only) {
         // throughput regime: the thread-per-pair Miller kernel (Karatsuba towers, saturated limbs) does ~1.45x more
         // pairs/s than the machine once the GPU is full; its raw product is handed to the machine for the
@@ -846,8 +931,11 @@ size_t pairing_work_bytes(bgls_ctx* ctx, int curve, size_t n) {
     const size_t t = align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
     const size_t m = mach_work_for(curve, n);
     if (ctx->thread_engine) return t;
-    if (n >= MHYBRID && !ctx->machine_only) return t + align_up(12 * fp_bytes(curve)) + mach_work_for(curve, 1);
-    return m > t ? m : t;
+    // the engine is chosen per call (load dependent): the scratch must fit whichever runs
+    const size_t sv = align_up(slot_blocks(n) * 12 * fp_bytes(curve)) + mach_work_for(curve, slot_blocks(n));
+    size_t w = m > t ? m : t;
+    if (n >= MHYBRID && !ctx->machine_only) w = std::max(w, t + align_up(12 * fp_bytes(curve)) + mach_work_for(curve, 1));
+    return std::max(w, sv);
 }
 
 // Acquires an execution slot for the duration of one API call.
@@ -856,6 +944,9 @@ size_t pairing_work_bytes(bgls_ctx* ctx, int curve, size_t n) {
 //   waits for that stream, so scratch is never shared by work that is not stream-ordered.
 struct SlotLock {
     Slot* s = nullptr;
+    cudaStream_t user = nullptr;
+    bool dev = false;
+    // host-buffer call: any free slot, work runs on the slot's own stream
     explicit SlotLock(bgls_ctx* c) {
         const unsigned start = c->rr.fetch_add(1);
         for (int i = 0; i < NSLOT && !s; i++) {
@@ -863,17 +954,20 @@ struct SlotLock {
             if (t->mu.try_lock()) s = t;
         }
         if (!s) { s = &c->slots[start % NSLOT]; s->mu.lock(); }
-        cudaStream_t prev = nullptr;
         bool had = false;
         {
             std::lock_guard<std::mutex> lk(c->own_mu);
             had = s->owned;
-            prev = s->owner;
             s->owned = false;
+            s->owner = nullptr;
         }
-        if (had) cudaStreamSynchronize(prev);
+        // the scratch may still be in use by device-resident work: order this call's stream after the event that the last
+        // such call recorded (no stream handle of the caller is kept or touched)
+        if (had) cudaStreamWaitEvent(s->stream, s->ev_done, 0);
     }
-    SlotLock(bgls_ctx* c, cudaStream_t user) {
+    // device-resident call: the slot ordered on the caller's stream; a slot taken over from other work first waits (on the
+    // device) for the event recorded at the end of that work, so scratch is never shared by work that is not ordered
+    SlotLock(bgls_ctx* c, cudaStream_t user_) : user(user_), dev(true) {
         {
             std::lock_guard<std::mutex> lk(c->own_mu);
             for (int i = 0; i < NSLOT && !s; i++)
@@ -892,10 +986,18 @@ struct SlotLock {
             s->owned = true;
             s->owner = user;
         }
-        if (had && prev != user) cudaStreamSynchronize(prev);
-        else if (!had) cudaStreamSynchronize(s->stream);
+        if (had && prev != user) cudaStreamWaitEvent(user, s->ev_done, 0);
+        else if (!had) {
+            // last used by a host-buffer call (synchronous: its stream is idle) or never
+            cudaEventRecord(s->ev_done, s->stream);
+            cudaStreamWaitEvent(user, s->ev_done, 0);
+        }
+        s->last_use_us.store(now_us(), std::memory_order_relaxed);
     }
-    ~SlotLock() { s->mu.unlock(); }
+    ~SlotLock() {
+        if (dev) cudaEventRecord(s->ev_done, user);   // everything this call enqueued precedes the event
+        s->mu.unlock();
+    }
     SlotLock(const SlotLock&) = delete;
     SlotLock& operator=(const SlotLock&) = delete;
 };
@@ -920,6 +1022,7 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
              cudaStreamCreateWithFlags(&sl.aux, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaHostAlloc((void**)&sl.hres, HRES_BYTES, cudaHostAllocDefault) == cudaSuccess;
     }
     if (!ok) {
@@ -928,6 +1031,7 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
             if (sl.aux) cudaStreamDestroy(sl.aux);
             if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
             if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+            if (sl.ev_done) cudaEventDestroy(sl.ev_done);
             if (sl.hres) cudaFreeHost(sl.hres);
         }
         delete ctx;
@@ -936,6 +1040,7 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     const char* eng = getenv("BGLS_ENGINE");
     ctx->thread_engine = eng && std::string(eng) == "thread";
     ctx->machine_only = eng && std::string(eng) == "machine";
+    ctx->engine = ctx->thread_engine ? ENGINE_THREAD : ctx->machine_only ? ENGINE_MACHINE : (eng && std::string(eng) == "slot") ? ENGINE_SLOT : ENGINE_AUTO;
     const char* mil = getenv("BGLS_MILLER");
     ctx->miller16 = mil && std::string(mil) == "m16";
     const char* mw = getenv("BGLS_MIN_WPB");
@@ -945,6 +1050,8 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     if (ctx->sms <= 0) ctx->sms = 148;
     int rc = upload_mach<mtab::BN254_M, mtab::BN254_M_T, mtab::BN254_F, mtab::BN254_F_T, mtab::BN254_MP, mtab::BN254_MP_T>(ctx, ctx->mach[0]);
     if (!rc) rc = upload_mach<mtab::BLS381_M, mtab::BLS381_M_T, mtab::BLS381_F, mtab::BLS381_F_T, mtab::BLS381_MP, mtab::BLS381_MP_T>(ctx, ctx->mach[1]);
+    if (!rc) rc = upload_slot<BN254, SlotBN>(ctx, ctx->sloteng[0]);
+    if (!rc) rc = upload_slot<BLS381, SlotBLS>(ctx, ctx->sloteng[1]);
     if (rc) {
         bgls_ctx_destroy(ctx);
         return rc;
@@ -963,8 +1070,11 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
         if (sl.aux) cudaStreamDestroy(sl.aux);
         if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
         if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     for (auto& d : ctx->mach)
+        if (d.blob) cudaFree(d.blob);
+    for (auto& d : ctx->sloteng)
         if (d.blob) cudaFree(d.blob);
     for (int r = 0; r < (int)ctx->xch.peer.size(); r++)
         if (ctx->xch.peer[r] && r != ctx->xch.rank) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
@@ -1027,6 +1137,11 @@ int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s) {
 static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, int do_final,
                         uint8_t* out, int* flag) {
     if (!ctx || !curve_ok(curve) || !out || (n && (!g1 || !g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    struct Busy {   // load estimate of use_slot_engine
+        bgls_ctx* c;
+        explicit Busy(bgls_ctx* c_) : c(c_) { c->host_calls++; }
+        ~Busy() { c->host_calls--; }
+    } busy(ctx);
     SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(n * 2 * F), b2 = align_up(n * 4 * F), bo = align_up(12 * F + 16);
