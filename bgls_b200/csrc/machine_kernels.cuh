@@ -339,6 +339,69 @@ __global__ void __launch_bounds__(MFIN_THREADS) k_mach_finish(MachTables tb, con
     }
 }
 
+// Low-footprint final exponentiation for the throughput regime: the schedule tables stay in global memory (L2 / L1 hits)
+// and only the group file lives in shared memory (19 / 26 KB instead of 148 / 190 KB).  It runs as the tail of the slot
+// engine's Miller kernel (one launch per product: a dependent launch would stall the hardware queue its stream shares with
+// other streams, and a block that needs most of an SM's shared memory is starved while the GPU is full of small Miller
+// blocks) or as a one-warp kernel of its own.  About 0.1 ms slower than the staged kernel when it runs alone.
+struct MachFinishArgs {
+    MachTables tb;
+    const uint16_t* prog;
+    int plen;
+    uint8_t* out_gt;      // 12 F bytes (may be null)
+    int* flag32;          // is-identity flag (may be null)
+};
+// one warp; `sm`: at least F::NS * F::L words of shared memory; `in`: the value in machine form ([12][L] limbs)
+template <class F>
+__device__ __forceinline__ void mach_finish_warp(uint32_t* sm, const MachFinishArgs& a, const uint32_t* in) {
+    constexpr int L = F::L, FB = F::FP_BYTES;
+    static_assert(F::LANES == 32, "the final-exponentiation slot file is scheduled for 32-lane groups");
+    uint32_t* gbase = sm;
+    constexpr int CW = F::NCONST * L;
+    const int gl = threadIdx.x & 31;
+    for (int idx = gl; idx < CW; idx += 32) gbase[(idx % L) * F::NS + F::NSG + idx / L] = a.tb.consts[idx];
+    MachView<F> mv;
+    mv.gs = gbase;
+    if (gl < 12) {
+        uint32_t v[L];
+        const uint32_t* src = in + gl * L;
+#pragma unroll
+        for (int i = 0; i < L; i++) v[i] = __ldcg(src + i);
+        mach_store<F>(mv, F::FA0 + gl, v);
+    }
+    __syncwarp();
+    mach_run<F>(mv, a.tb, a.prog, a.plen, gl);
+    bool ok = true;
+    if (gl < 12) {
+        uint32_t v[L];
+        mach_load<F>(v, mv, F::OUT0 + gl);
+        const int k = gl >> 1, part = gl & 1;                       // coefficient of w^k, 0 = re, 1 = im
+        const int pos = k == 5 ? 0 : k == 3 ? 1 : k == 1 ? 2 : k == 4 ? 3 : k == 2 ? 4 : 5;  // GT order 5,3,1,4,2,0
+        bool z, one;
+        uint8_t bytes[FB];
+        mach_canon_be<F>(bytes, v, &z, &one);
+        if (a.out_gt) {
+            uint8_t* dst = a.out_gt + (size_t)(2 * pos + (part ? 0 : 1)) * FB;
+#pragma unroll
+            for (int i = 0; i < FB; i++) dst[i] = bytes[i];
+        }
+        ok = (gl == 0) ? one : z;
+    }
+    const unsigned okb = __ballot_sync(0xFFFFFFFFu, ok);
+    if (gl == 0 && a.flag32) *a.flag32 = (okb & 0xFFFu) == 0xFFFu;
+}
+template <class F> struct MachFinisher {   // tail of k_slot_miller (slotvm.cuh)
+    using Args = MachFinishArgs;
+    static constexpr size_t SMEM_BYTES = (size_t)F::NS * F::L * sizeof(uint32_t);
+    static constexpr int MACH_L = F::L;
+    __device__ __forceinline__ static void run(uint32_t* sm, const Args& a, const uint32_t* in) { mach_finish_warp<F>(sm, a, in); }
+};
+template <class F>
+__global__ void __launch_bounds__(32) k_mach_finish_lean(MachFinishArgs a, const uint32_t* __restrict__ in) {
+    extern __shared__ uint32_t sm[];
+    mach_finish_warp<F>(sm, a, in);
+}
+
 // ---------------------------------------------------------------- import: wire GT bytes -> machine form
 template <class M>
 __global__ void __launch_bounds__(MWPB * 32) k_mach_import(MachTables tb, const uint16_t* __restrict__ prog, int plen,

@@ -20,16 +20,17 @@
 
 namespace bgls {
 
-enum : uint32_t { SV_NOP = 0, SV_MUL, SV_SQR, SV_ADD, SV_SUB, SV_XI, SV_HALF, SV_CONJ, SV_NEG, SV_COPY };
+enum : uint32_t { SV_NOP = 0, SV_MUL, SV_SQR, SV_ADD, SV_SUB, SV_XI, SV_HALF, SV_CONJ, SV_NEG, SV_COPY, SV_SEL0, SV_SEL1 };
 constexpr uint32_t SV_CONST0 = 256;
 
 struct alignas(16) SvU4 { uint32_t x, y, z, w; };   // 16-byte unit of the slot file (uint4 on the device)
 
 template <class C, int NPB> struct SlotFile {
     static constexpr int N = C::N, W4 = 2 * N / 4;
-    SvU4* slots;          // pair slots
+    SvU4* slots;          // group slots
     const SvU4* consts;   // constants, [c][W4]
-    int q;                // pair index inside the block
+    int q;                // group index inside the block
+    uint32_t flags;       // bit j: pair j of the group has a point at infinity (SEL0 / SEL1)
 
     HD F2<C> load(uint32_t s) const {
         const SvU4* p;
@@ -118,6 +119,10 @@ template <class C, int NPB> HD void sv_exec(const SlotFile<C, NPB>& sf, uint32_t
         mp_neg<C>(r.c0.v, a.c0.v);
         mp_neg<C>(r.c1.v, a.c1.v);
         break;
+    case SV_SEL0:
+    case SV_SEL1:   // the line of a pair with a point at infinity is replaced by 1 (sb = index of the pair in its group)
+        r = (sf.flags >> sb) & 1u ? sf.load(SV_CONST0 + (kind == SV_SEL1 ? 1 : 0)) : a;
+        break;
     default:   // SV_COPY
         r = a;
         break;
@@ -155,15 +160,17 @@ template <class C> HD LN<C::N> sv_zero() {
     for (int i = 0; i < C::N; i++) z.v[i] = 0;
     return z;
 }
-// stores coordinate c (0: xP, 1: yP, 2: xQ.im, 3: xQ.re, 4: yQ.im, 5: yQ.re) of a pair into the state slots
-template <class C, class T, int NPB> HD void sv_store_coord(const SlotFile<C, NPB>& sf, int c, const LN<C::N>& v) {
+// stores coordinate c (0: xP, 1: yP, 2: xQ.im, 3: xQ.re, 4: yQ.im, 5: yQ.re) of pair j of the group into the state slots
+// (the per-pair state of pair j follows that of pair j - 1: TX TY TZ QX QY PX PY)
+template <class C, class T, int NPB> HD void sv_store_coord(const SlotFile<C, NPB>& sf, int j, int c, const LN<C::N>& v) {
+    const int o = 7 * j;
     switch (c) {
-    case 0: sf.store_fp(T::S_PX, 0, v); sf.store_fp(T::S_PX, 1, sv_zero<C>()); break;
-    case 1: sf.store_fp(T::S_PY, 0, v); sf.store_fp(T::S_PY, 1, sv_zero<C>()); break;
-    case 2: sf.store_fp(T::S_QX, 1, v); sf.store_fp(T::S_TX, 1, v); break;
-    case 3: sf.store_fp(T::S_QX, 0, v); sf.store_fp(T::S_TX, 0, v); break;
-    case 4: sf.store_fp(T::S_QY, 1, v); sf.store_fp(T::S_TY, 1, v); break;
-    default: sf.store_fp(T::S_QY, 0, v); sf.store_fp(T::S_TY, 0, v); break;
+    case 0: sf.store_fp(T::S_PX0 + o, 0, v); sf.store_fp(T::S_PX0 + o, 1, sv_zero<C>()); break;
+    case 1: sf.store_fp(T::S_PY0 + o, 0, v); sf.store_fp(T::S_PY0 + o, 1, sv_zero<C>()); break;
+    case 2: sf.store_fp(T::S_QX0 + o, 1, v); sf.store_fp(T::S_TX0 + o, 1, v); break;
+    case 3: sf.store_fp(T::S_QX0 + o, 0, v); sf.store_fp(T::S_TX0 + o, 0, v); break;
+    case 4: sf.store_fp(T::S_QY0 + o, 1, v); sf.store_fp(T::S_TY0 + o, 1, v); break;
+    default: sf.store_fp(T::S_QY0 + o, 0, v); sf.store_fp(T::S_TY0 + o, 0, v); break;
     }
 }
 // f <- 1
@@ -177,9 +184,21 @@ template <class T> HD int sv_wire_slot(int i) {
     return i == 0 ? T::S_F12 : i == 1 ? T::S_F11 : i == 2 ? T::S_F10 : i == 3 ? T::S_F02 : i == 4 ? T::S_F01 : T::S_F00;
 }
 
-// shared-memory footprint (bytes) of one block: code words, constants, slot file, per-pair flags
-template <class C, class T, int NPB> constexpr size_t sv_smem_bytes() {
-    return ((size_t)T::NWORDS * 4 + 15) / 16 * 16 + (size_t)T::NCONST * (2 * C::N / 4) * 16 + (size_t)T::NSLOT * (2 * C::N / 4) * NPB * 16;
+// shared-memory footprint (bytes) of one block: constants, slot file, per-group flags
+template <class C, class T, int NPB> constexpr size_t sv_smem_bytes() {   // NPB: groups per block
+    return (size_t)T::NCONST * (2 * C::N / 4) * 16 + (size_t)T::NSLOT * (2 * C::N / 4) * NPB * 16;
+}
+
+// scratch of the in-launch product tree over nb block values with fan-in `fan`: words of all levels / number of tickets
+inline size_t sv_tree_words(size_t nb, size_t fan, size_t n_limbs) {
+    size_t w = 0;
+    for (size_t c = nb; c > 1; c = (c + fan - 1) / fan) w += c * 12 * n_limbs;
+    return w;
+}
+inline size_t sv_tree_counters(size_t nb, size_t fan) {
+    size_t k = 0;
+    for (size_t c = nb; c > 1; c = (c + fan - 1) / fan) k += (c + fan - 1) / fan;
+    return k;
 }
 
 #if defined(__CUDACC__)
@@ -188,91 +207,239 @@ struct SvTables {          // device copies of one table set (code, program offs
     const uint32_t* offs;
     const uint8_t* seq;
     const uint32_t* consts;
+    const uint32_t* mach_r;   // 2^(28 L) mod p (L: limbs of the machine's 28-bit form), plain N 32-bit limbs
 };
 
 // runs the code words [lo, hi) : one operation per lane and round; the only instance of the interpreter in a kernel
 template <class C, int NPB, int G>
-__device__ __noinline__ void sv_run(SvU4* slots, const SvU4* consts, int q, const uint32_t* code, uint32_t lo, uint32_t hi, int gl, bool act) {
-    const SlotFile<C, NPB> sf{slots, consts, q};
+__device__ __noinline__ void sv_run(SvU4* slots, const SvU4* consts, int q, uint32_t flags, const uint32_t* code, uint32_t lo, uint32_t hi,
+                                    int gl, bool act) {
+    const SlotFile<C, NPB> sf{slots, consts, q, flags};
     for (uint32_t w = lo; w < hi; w += G) {
-        if (act) sv_exec<C, NPB>(sf, code[w + gl]);
+        if (act) sv_exec<C, NPB>(sf, __ldg(code + w + gl));
         if (G > 1) __syncwarp();
     }
 }
 
-// Miller loops of the pairs [blockIdx.x * NPB, ...) and their product: one GT wire record (raw Miller product, no
-// final exponentiation) per block.  WPB warps per block, G lanes per pair, NPB = WPB * 32 / G pairs per block.
-template <class C, class T, int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
-                                                          size_t n, uint8_t* __restrict__ partials) {
-    constexpr int N = C::N, FB = C::FP_BYTES, G = T::G, NPB = WPB * 32 / G, W4 = 2 * N / 4;
-    extern __shared__ uint4 sv_sm[];
-    uint32_t* code = (uint32_t*)sv_sm;
-    SvU4* consts = (SvU4*)(sv_sm + (T::NWORDS * 4 + 15) / 16);
-    SvU4* slots = consts + T::NCONST * W4;
-    for (int i = threadIdx.x; i < T::NWORDS; i += blockDim.x) code[i] = tb.code[i];
-    for (int i = threadIdx.x; i < T::NCONST * 2 * N; i += blockDim.x) ((uint32_t*)consts)[i] = tb.consts[i];
-    const int q = threadIdx.x / G, gl = threadIdx.x % G;
-    const size_t first = (size_t)blockIdx.x * NPB;
-    const size_t pair = first + q;
-    const int npairs = (int)(n - first < (size_t)NPB ? n - first : (size_t)NPB);
-    const SlotFile<C, NPB> sf{slots, consts, q};
-    // ---- inputs: G1 = x || y, G2 = x_im || x_re || y_im || y_re (big-endian); coordinate c is converted by lane c % G
-    uint32_t anyp = 0, anyq = 0, flag = 0;
-    if (pair < n) {
-        const uint8_t* r1 = g1 + pair * 2 * FB;
-        const uint8_t* r2 = g2 + pair * 4 * FB;
+// product tree over the accumulators of the block's first `ngroups` groups: f_q <- f_q * f_{q + st}; group 0 ends up with
+// the product.  Every thread of the block must call it.
+template <class C, class T, int NPB>
+__device__ __forceinline__ void sv_block_tree(SvU4* slots, const SvU4* consts, const SvTables& tb, int q, int gl, int ngroups) {
+    constexpr int G = T::G;
+    const SlotFile<C, NPB> sf{slots, consts, q, 0};
+    const uint32_t mlo = tb.offs[T::P_MUL12], mhi = tb.offs[T::P_MUL12 + 1];
 #pragma unroll 1
-        for (int c = gl; c < 6; c += G) {
-            const uint8_t* src = c < 2 ? r1 + c * FB : r2 + (c - 2) * FB;
-            const LN<N> v = sv_fp_from_be<C>(src);
+    for (int st = 1; st < NPB; st <<= 1) {
+        __syncthreads();
+        if (st >= ngroups) break;     // uniform over the block
+        const bool act = (q & (2 * st - 1)) == 0 && q + st < ngroups;
+        if (act) {
+            const SlotFile<C, NPB> pf{slots, consts, q + st, 0};
+            for (int k = gl; k < 6; k += G) sf.store(T::S_G00 + k, pf.load(T::S_F00 + k));
+        }
+        if (G > 1) __syncwarp();
+        sv_run<C, NPB, G>(slots, consts, q, 0, tb.code, mlo, mhi, gl, act);
+    }
+    __syncthreads();
+}
+// Internal form of an Fp12 value between the slot engine's kernels: the 6 accumulator slots F00..F12 as they are
+// (canonical Montgomery limbs, R = 2^(32 N)), 12 N words per value.
+// mach_l > 0: the block's value leaves in the form the machine's final-exponentiation kernel reads instead
+// (machine_kernels.cuh: index 2 k + part for the coefficient of w^k, mach_l limbs of 28 bits of x * 2^(28 mach_l) mod p).
+template <class C, class T, int NPB>
+__device__ __forceinline__ void sv_emit_value(SvU4* slots, const SvU4* consts, const SvTables& tb, uint32_t* out, int mach_l) {
+    constexpr int N = C::N;
+    if (threadIdx.x >= 12) return;
+    const SlotFile<C, NPB> p0{slots, consts, 0, 0};
+    if (mach_l == 0) {
+        const int slot = T::S_F00 + (threadIdx.x >> 1), half = threadIdx.x & 1;
+        const LN<N> v = p0.load_fp(slot, half);
+#pragma unroll
+        for (int i = 0; i < N; i++) out[threadIdx.x * N + i] = v.v[i];
+        return;
+    }
+    const int k = threadIdx.x >> 1, part = threadIdx.x & 1;                       // coefficient of w^k, 0 = re, 1 = im
+    const int slot = (k & 1) ? T::S_F10 + (k >> 1) : T::S_F00 + (k >> 1);       // w^k: k even -> F0{k/2}, k odd -> F1{(k-1)/2}
+    LN<N> r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = tb.mach_r[i];
+    const LN<N> x = sat_fp_mul<C>(p0.load_fp(slot, part), r);                     // x * 2^(28 L) mod p, canonical
+    uint32_t* o = out + threadIdx.x * mach_l;
+    for (int i = 0; i < mach_l; i++) {
+        const int bit = 28 * i, w = bit >> 5, sh = bit & 31;
+        const uint32_t lo = x.v[w], hi = w + 1 < N ? x.v[w + 1] : 0u;
+        o[i] = (sh ? ((lo >> sh) | (hi << (32 - sh))) : lo) & 0x0FFFFFFFu;
+    }
+}
+
+// Miller loops of the pairs [blockIdx.x * NPB * K, ...) and the product of ALL the launch's pairs: one Fp12 value (raw Miller
+// product, no final exponentiation) in `mach_out` (machine form when mach_l > 0, else internal form).  `partials`: scratch
+// for the tree levels (sv_tree_words), `counters`: zero-initialised tickets (sv_tree_counters), left zero.  WPB warps per block, G lanes per group of K pairs (one shared Miller
+// accumulator), NPB = WPB * 32 / G groups per block.
+// FIN: what the block that ends up with the product does with it -- SvNoFinish: nothing more (the value is in `mach_out`);
+// MachFinisher<F> (machine_kernels.cuh): the final exponentiation, or the plain export, in the same launch.
+struct SvNoFinish {
+    struct Args { int unused; };
+    static constexpr size_t SMEM_BYTES = 0;
+    __device__ __forceinline__ static void run(uint32_t*, const Args&, const uint32_t*) {}
+};
+template <class C, class T, int WPB, class FIN>
+__global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
+                                                          size_t n, uint32_t* __restrict__ partials, unsigned* __restrict__ counters,
+                                                          uint32_t* __restrict__ mach_out, int mach_l, typename FIN::Args fin,
+                                                          unsigned long long* __restrict__ trace) {
+    constexpr int N = C::N, FB = C::FP_BYTES, G = T::G, K = T::K, NPB = WPB * 32 / G, W4 = 2 * N / 4;
+    extern __shared__ uint4 sv_sm[];
+    unsigned long long t_start = 0;
+    if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    // the program words stay in global memory: a few KB read by every warp of the GPU, i.e. L1 hits; staging them per
+    // block cost 3 KB of shared memory (a fifth of a block's footprint at 8 lanes per group)
+    const uint32_t* code = tb.code;
+    SvU4* consts = (SvU4*)sv_sm;
+    SvU4* slots = consts + T::NCONST * W4;
+    for (int i = threadIdx.x; i < T::NCONST * 2 * N; i += blockDim.x) ((uint32_t*)consts)[i] = tb.consts[i];
+    // lane -> (group, lane of the group): the 32 / G groups of a warp are interleaved, so that the lanes of a quarter
+    // warp hold the SAME lane index of consecutive groups: they run the same operation on the same slot and their
+    // 16-byte accesses are consecutive (conflict free; with lane = group * G + index every access was a G-way conflict)
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int q = (threadIdx.x >> 5) * GPW + lane % GPW, gl = lane / GPW;
+    const size_t first = (size_t)blockIdx.x * NPB * K;                  // first pair of the block
+    const size_t ngroups_left = (n - first + K - 1) / K;
+    const int ngroups = (int)(ngroups_left < (size_t)NPB ? ngroups_left : (size_t)NPB);
+    SlotFile<C, NPB> sf{slots, consts, q, 0};
+    // ---- inputs: G1 = x || y, G2 = x_im || x_re || y_im || y_re (big-endian); coordinate c of pair j is converted by lane
+    // (6 j + c) % G.  A point is infinity when its record is all zero (or carries the bls12 infinity flag).
+    uint32_t anyp = 0, anyq = 0, flag = 0;   // bit j: pair j has a non-zero G1 / G2 coordinate / an infinity flag
+#pragma unroll 1
+    for (int t = gl; t < 6 * K; t += G) {
+        const int j = t / 6, c = t % 6;
+        const size_t pair = first + (size_t)q * K + j;
+        LN<N> v = sv_zero<C>();
+        if (pair < n) {
+            const uint8_t* src = c < 2 ? g1 + pair * 2 * FB + c * FB : g2 + pair * 4 * FB + (c - 2) * FB;
+            v = sv_fp_from_be<C>(src);
             uint32_t any = 0;
 #pragma unroll
             for (int i = 0; i < N; i++) any |= v.v[i];
-            if (c < 2) anyp |= any; else anyq |= any;
-            if (!C::IS_BN && (c == 0 || c == 2) && (src[0] & 0x40)) flag = 1;
-            sv_store_coord<C, T, NPB>(sf, c, v);
+            if (any) { if (c < 2) anyp |= 1u << j; else anyq |= 1u << j; }
+            if (!C::IS_BN && (c == 0 || c == 2) && (src[0] & 0x40)) flag |= 1u << j;
         }
+        sv_store_coord<C, T, NPB>(sf, j, c, v);
     }
-    // a point is infinity when its record is all zero (or carries the bls12 infinity flag): the pair contributes 1
 #pragma unroll
-    for (int o = 1; o < G; o <<= 1) {
+    for (int o = GPW; o < 32; o <<= 1) {   // over the lanes of the group
         anyp |= __shfl_xor_sync(0xFFFFFFFFu, anyp, o);
         anyq |= __shfl_xor_sync(0xFFFFFFFFu, anyq, o);
         flag |= __shfl_xor_sync(0xFFFFFFFFu, flag, o);
     }
-    const bool inf = pair >= n || anyp == 0 || anyq == 0 || flag != 0;
-    __syncthreads();   // code and constants staged, inputs stored
-    if (gl == 0) sf.store(T::S_TZ, sf.load(SV_CONST0 + 1));
+    const uint32_t inf = (~(anyp & anyq) | flag) & ((1u << K) - 1);     // pairs beyond n have all-zero coordinates
+    sf.flags = inf;
+    __syncthreads();   // constants staged, inputs stored
+    for (int j = gl; j < K; j += G) sf.store(T::S_TZ0 + 7 * j, sf.load(SV_CONST0 + 1));
     __syncwarp();
     // ---- the Miller loop: a sequence of programs
 #pragma unroll 1
     for (int s = 0; s < T::SEQ_LEN; s++) {
         const uint32_t pid = tb.seq[s];
-        sv_run<C, NPB, G>(slots, consts, q, code, tb.offs[pid], tb.offs[pid + 1], gl, true);
+        sv_run<C, NPB, G>(slots, consts, q, inf, code, tb.offs[pid], tb.offs[pid + 1], gl, true);
     }
-    if (inf && gl == 0) sv_set_one<C, T, NPB>(sf);
-    // ---- product tree over the block's pairs: f_q <- f_q * f_{q + st}
-    const uint32_t mlo = tb.offs[T::P_MUL12], mhi = tb.offs[T::P_MUL12 + 1];
+    if (K == 1 && inf && gl == 0) sv_set_one<C, T, NPB>(sf);            // K > 1: the lines of such pairs were replaced by 1
+    sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, ngroups);
+    if (trace && threadIdx.x == 0) {   // BGLS_TRACE: (start ns, end ns, SM) of every Miller block, for timeline reconstruction
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned long long slot = atomicAdd(trace, 1ull);
+        if (slot < (1ull << 20)) { trace[1 + 3 * slot] = t_start; trace[2 + 3 * slot] = t_end; trace[3 + 3 * slot] = smid; }
+    }
+    // ---- cross-block product tree inside the same launch: a block stores its value, and the LAST block of every group of
+    // FAN blocks to arrive (atomic ticket) multiplies the group's values and moves one level up; the block that ends up
+    // with the last value writes it in the machine's form.  No dependent kernel is needed for the tree: with many
+    // products in flight every dependent launch in a stream stalls the hardware queue it shares with other streams
+    // (measured: 2.6 M pairings/s with three tree launches per product, 4.1 M without them).
+    constexpr int FAN = 2 * NPB;
+    __shared__ int s_last;
+    size_t count = gridDim.x, idx = blockIdx.x;
+    uint32_t* lvl = partials;
+    unsigned* cnt = counters;
 #pragma unroll 1
-    for (int st = 1; st < NPB; st <<= 1) {
+    while (count > 1) {
+        sv_emit_value<C, T, NPB>(slots, consts, tb, lvl + idx * 12 * N, 0);
+        __threadfence();
         __syncthreads();
-        if (st >= npairs) break;     // uniform over the block
-        const bool act = (q & (2 * st - 1)) == 0 && q + st < npairs;
-        if (act) {
-            const SlotFile<C, NPB> pf{slots, consts, q + st};
-            for (int k = gl; k < 6; k += G) sf.store(T::S_G00 + k, pf.load(T::S_F00 + k));
+        const size_t grp = idx / FAN;
+        const int size = (int)(count - grp * FAN < (size_t)FAN ? count - grp * FAN : (size_t)FAN);
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(cnt + grp, 1u);
+            s_last = t == (unsigned)(size - 1);
+            if (s_last) cnt[grp] = 0;      // ready for the next launch
         }
-        if (G > 1) __syncwarp();
-        sv_run<C, NPB, G>(slots, consts, q, code, mlo, mhi, gl, act);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        // group q: F <- value 2q, G <- value 2q + 1 of this group of blocks
+        for (int t = gl; t < 24; t += G) {
+            const int which = t / 12, fi = t % 12, v = 2 * q + which;
+            if (v < size) {
+                LN<N> x;
+                const uint32_t* src = lvl + (grp * FAN + v) * 12 * N + fi * N;
+#pragma unroll
+                for (int i = 0; i < N; i++) x.v[i] = __ldcg(src + i);
+                sf.store_fp((which ? T::S_G00 : T::S_F00) + (fi >> 1), fi & 1, x);
+            }
+        }
+        __syncthreads();
+        sv_run<C, NPB, G>(slots, consts, q, 0, code, tb.offs[T::P_MUL12], tb.offs[T::P_MUL12 + 1], gl, 2 * q + 1 < size);
+        sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, (size + 1) / 2);
+        const size_t groups = (count + FAN - 1) / FAN;
+        lvl += count * 12 * N;
+        cnt += groups;
+        idx = grp;
+        count = groups;
+    }
+    sv_emit_value<C, T, NPB>(slots, consts, tb, mach_out, mach_l);
+    if (FIN::SMEM_BYTES) {   // the final exponentiation runs on the first warp of this block, over the same shared memory
+        __threadfence_block();
+        __syncthreads();
+        if (threadIdx.x < 32) FIN::run((uint32_t*)sv_sm, fin, mach_out);
+    }
+}
+
+// One level of the product tree over Fp12 values in the internal form: every block multiplies up to 2 * NPB values into one.
+template <class C, class T, int WPB>
+__global__ void __launch_bounds__(WPB * 32) k_slot_reduce(SvTables tb, const uint32_t* __restrict__ in, size_t m, uint32_t* __restrict__ out,
+                                                          int mach_l) {
+    constexpr int N = C::N, G = T::G, NPB = WPB * 32 / G, W4 = 2 * N / 4;
+    extern __shared__ uint4 sv_sm[];
+    SvU4* consts = (SvU4*)sv_sm;
+    SvU4* slots = consts + T::NCONST * W4;
+    for (int i = threadIdx.x; i < T::NCONST * 2 * N; i += blockDim.x) ((uint32_t*)consts)[i] = tb.consts[i];
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int q = (threadIdx.x >> 5) * GPW + lane % GPW, gl = lane / GPW;
+    const size_t first = (size_t)blockIdx.x * 2 * NPB;
+    const size_t left = m - first;
+    const int nvals = (int)(left < (size_t)(2 * NPB) ? left : (size_t)(2 * NPB));
+    const int ngroups = (nvals + 1) / 2;
+    const SlotFile<C, NPB> sf{slots, consts, q, 0};
+    // group q: F <- value 2q, G <- value 2q + 1
+    for (int t = gl; t < 24; t += G) {
+        const int which = t / 12, idx = t % 12;   // which value, which Fp of it
+        const int v = 2 * q + which;
+        if (v < nvals) {
+            LN<N> x;
+            const uint32_t* src = in + (first + v) * 12 * N + idx * N;
+#pragma unroll
+            for (int i = 0; i < N; i++) x.v[i] = src[i];
+            sf.store_fp((which ? T::S_G00 : T::S_F00) + (idx >> 1), idx & 1, x);
+        }
     }
     __syncthreads();
-    // ---- wire record of the block's product (pair 0): w-powers 5,3,1,4,2,0, each (im, re)
-    if (threadIdx.x < 12) {
-        const int i = threadIdx.x >> 1, part = threadIdx.x & 1;          // position i, part 0 = im, 1 = re
-        const SlotFile<C, NPB> p0{slots, consts, 0};
-        sv_fp_to_be<C>(partials + ((size_t)blockIdx.x * 12 + threadIdx.x) * FB, p0.load_fp(sv_wire_slot<T>(i), part ? 0 : 1));
-    }
+    sv_run<C, NPB, G>(slots, consts, q, 0, tb.code, tb.offs[T::P_MUL12], tb.offs[T::P_MUL12 + 1], gl, 2 * q + 1 < nvals);
+    sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, ngroups);
+    sv_emit_value<C, T, NPB>(slots, consts, tb, out + (size_t)blockIdx.x * 12 * (mach_l ? mach_l : N), mach_l);
 }
 #endif
 

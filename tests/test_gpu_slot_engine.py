@@ -1,4 +1,4 @@
-"""Slot engine (bgls_b200/csrc/slotvm.cuh: saturated limbs, lazy reduction, 4 lanes per pair) through the C ABI against the
+"""Slot engine (bgls_b200/csrc/slotvm.cuh: saturated limbs, lazy reduction, 8 lanes per group of 2 pairs) through the C ABI against the
 oracle: the engine behind `PairingProduct` (/root/reference/curves/curve.go:125-170) whenever several products are in
 flight or one product is large.  BGLS_ENGINE=slot forces it at every size."""
 import os
@@ -30,7 +30,7 @@ def sctx():
 
 
 @pytest.mark.parametrize("cid,c", CURVES)
-@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 33, 100, 1025])
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 16, 17, 33, 100, 1025])
 def test_slot_product_bit_exact(sctx, cid, c, n):
     """GT bytes of random (rejecting) products equal the oracle's: ragged block sizes, one to many blocks."""
     rng = random.Random(7000 * cid + n)

@@ -40,34 +40,44 @@ def test_tables_are_current():
 
 
 @pytest.mark.parametrize("cid,c", CURVES)
-@pytest.mark.parametrize("g", G.LANES)
-def test_programs_over_big_integers(cid, c, g):
-    eng = G.engine(CFG[cid], g)
+@pytest.mark.parametrize("g,k", G.SHAPES)
+def test_programs_over_big_integers(cid, c, g, k):
+    eng = G.engine(CFG[cid], g, k)
     emu = G.Emu(eng)
     rng = random.Random(5 + cid)
-    P = c.g1_mul(c.g1, rng.randrange(1, c.r))
-    Q = c.g2_mul(c.g2, rng.randrange(1, c.r))
-    raw_c = C.miller_product(cid, c.marshal_g1(P), c.marshal_g2(Q), 1)
-    # binary loop: the raw Miller value is the oracle's, bit for bit (same formulas as oracle/pairing_impl.h)
-    assert c.marshal_gt(emu.miller(P, Q, use_naf=False)) == raw_c
-    # released sequence (NAF on altbn128): equal after the final exponentiation
-    assert C.fp12_product(cid, c.marshal_gt(emu.miller(P, Q, use_naf=True)), 1, True) == C.fp12_product(cid, raw_c, 1, True)
+    for trial in range(3 if k > 1 else 1):
+        Ps = [c.g1_mul(c.g1, rng.randrange(1, c.r)) for _ in range(k)]
+        Qs = [c.g2_mul(c.g2, rng.randrange(1, c.r)) for _ in range(k)]
+        if trial == 1:
+            Ps[k - 1] = None      # a point at infinity in a group that shares its accumulator: the pair contributes 1
+        if trial == 2:
+            Qs[0] = None
+        g1 = b"".join(c.marshal_g1(P) for P in Ps)
+        g2 = b"".join(c.marshal_g2(Q) for Q in Qs)
+        raw_c = C.miller_product(cid, g1, g2, k)
+        if k == 1:
+            # binary loop: the raw Miller value is the oracle's, bit for bit (same formulas as oracle/pairing_impl.h)
+            assert c.marshal_gt(emu.miller(Ps, Qs, use_naf=False)) == raw_c
+        # released sequence (NAF on altbn128; shared accumulator for k > 1): equal after the final exponentiation
+        for naf in (False, True):
+            assert C.fp12_product(cid, c.marshal_gt(emu.miller(Ps, Qs, use_naf=naf)), 1, True) == C.fp12_product(cid, raw_c, 1, True)
     for name, s in eng.progs.items():
         G.check_hazards(s.rounds, g)
         assert s.nslots <= eng.nslots < G.CONST0
 
 
 @pytest.mark.parametrize("cid,c", CURVES)
-@pytest.mark.parametrize("g", G.LANES)
-def test_interpreter_on_host(emu_lib, cid, c, g):
+@pytest.mark.parametrize("g,k", G.SHAPES)
+def test_interpreter_on_host(emu_lib, cid, c, g, k):
     nb = c.nbytes
     rng = random.Random(100 + cid)
-    for n in (1, 3, 5, 8):
+    for n in (1, 3, 5, 8, 8 * k - 1):
         g1, g2 = make_aggregate(cid, c, n - 1, rng, nthreads=4) if n > 1 else (c.marshal_g1(c.g1), c.marshal_g2(c.g2))
-        if n == 5:   # an infinity pair inside
+        if n == 5:   # an infinity pair inside (G1 side), and one on the G2 side
             g1 = g1[:2 * nb] + bytes(2 * nb) + g1[4 * nb:]
+            g2 = g2[:4 * nb * 2] + bytes(4 * nb) + g2[4 * nb * 3:]
         out = ctypes.create_string_buffer(12 * nb)
-        assert emu_lib.emu_slot_miller_product(cid, g, g1, g2, n, out) == 0
+        assert emu_lib.emu_slot_miller_product(cid, g, k, g1, g2, n, out) == 0
         assert C.fp12_product(cid, out.raw, 1, True) == C.pairing_product(cid, g1, g2, n, 4, 0)
 
 

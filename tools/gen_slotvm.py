@@ -10,6 +10,12 @@ checked on a CPU by evaluating it over big integers (`Emu`, used by tests/test_s
 Operations (32-bit words: kind | dst << 5 | a << 14 | b << 23; slots >= CONST0 are block-shared constants):
     MUL d = a*b   SQR d = a^2   ADD d = a+b   SUB d = a-b   XI d = xi*a   HALF d = a/2   CONJ d = conj(a)
     NEG d = -a    COPY d = a    NOP
+    SEL0 / SEL1 d = flag(j) ? 0 / 1 : a   (j = b field: sub-pair of the group; flag = the pair has a point at infinity)
+
+K pairs may share one Miller accumulator (K = 2 with 8 lanes per group): every iteration squares f once and multiplies
+the K lines into it -- the squaring is 12 of the 37 Fp2 multiplications of a doubling iteration, and a group of K
+pairs needs far fewer slots per pair, i.e. more resident warps.  A pair with a point at infinity must contribute 1:
+its line is replaced by 1 through SEL0 / SEL1 (per-pair flags in shared memory).
 
 Formulas (homogeneous projective doubling / mixed addition with lines, Karatsuba towers, sparse line
 multiplication) are those of pairing.cuh / field.cuh, i.e. of oracle/pairing_impl.h, so the raw Miller value of the
@@ -23,10 +29,10 @@ from __future__ import annotations
 import os
 import sys
 
-NOP, MUL, SQR, ADD, SUB, XI, HALF, CONJ, NEG, COPY = range(10)
-KIND_NAMES = ["NOP", "MUL", "SQR", "ADD", "SUB", "XI", "HALF", "CONJ", "NEG", "COPY"]
+NOP, MUL, SQR, ADD, SUB, XI, HALF, CONJ, NEG, COPY, SEL0, SEL1 = range(12)
+KIND_NAMES = ["NOP", "MUL", "SQR", "ADD", "SUB", "XI", "HALF", "CONJ", "NEG", "COPY", "SEL0", "SEL1"]
 HEAVY = (MUL, SQR)
-COST = {MUL: 14, SQR: 11, ADD: 1, SUB: 1, XI: 3, HALF: 1, CONJ: 1, NEG: 1, COPY: 1, NOP: 0}
+COST = {MUL: 14, SQR: 11, ADD: 1, SUB: 1, XI: 3, HALF: 1, CONJ: 1, NEG: 1, COPY: 1, SEL0: 1, SEL1: 1, NOP: 0}
 CONST0 = 256
 
 BN_P = 21888242871839275222246405745257275088696311157297823662689037894645226208583
@@ -101,10 +107,10 @@ BLS = Cfg("bls12-381", "BLS381", BLS_P, 12, (1, 1), "M", 4, False)
 
 
 class Val:
-    __slots__ = ("id", "kind", "a", "b", "state", "users", "prio", "round", "lane", "slot", "last")
+    __slots__ = ("id", "kind", "a", "b", "state", "users", "prio", "round", "lane", "slot", "last", "imm")
 
-    def __init__(self, id, kind, a=None, b=None, state=None):
-        self.id, self.kind, self.a, self.b, self.state = id, kind, a, b, state
+    def __init__(self, id, kind, a=None, b=None, state=None, imm=0):
+        self.id, self.kind, self.a, self.b, self.state, self.imm = id, kind, a, b, state, imm
         self.users = []
         self.slot = None
 
@@ -119,8 +125,8 @@ class Builder:
         self.outputs = {}   # state name -> Val
         self.consts = {}    # const name -> Val
 
-    def _new(self, kind, a=None, b=None, state=None):
-        v = Val(len(self.vals), kind, a, b, state)
+    def _new(self, kind, a=None, b=None, state=None, imm=0):
+        v = Val(len(self.vals), kind, a, b, state, imm)
         self.vals.append(v)
         for x in (a, b):
             if x is not None:
@@ -150,6 +156,8 @@ class Builder:
     def conj(self, a): return self._new(CONJ, a)
     def neg(self, a): return self._new(NEG, a)
     def copy(self, a): return self._new(COPY, a)
+    def sel0(self, a, j): return self._new(SEL0, a, imm=j)
+    def sel1(self, a, j): return self._new(SEL1, a, imm=j)
     def dbl(self, a): return self.add(a, a)
     def triple(self, a): return self.add(self.add(a, a), a)
 
@@ -261,16 +269,19 @@ class Builder:
         return (X3, Y3, Z3), (ly, lx, lc)
 
 
-STATE = ["F00", "F01", "F02", "F10", "F11", "F12", "TX", "TY", "TZ", "QX", "QY", "PX", "PY", "NQY",
-         "G00", "G01", "G02", "G10", "G11", "G12"]
-# F: Miller accumulator ((F00,F01,F02),(F10,F11,F12)); T: projective point; Q: affine G2 input; PX = (xP, 0), PY = (yP, 0);
-# NQY = -QY (NAF subtraction steps); G: second Fp12 operand of the product tree (aliases temporaries, see below)
 FSLOTS = (("F00", "F01", "F02"), ("F10", "F11", "F12"))
 GSLOTS = (("G00", "G01", "G02"), ("G10", "G11", "G12"))
+PAIR_STATE = ("TX", "TY", "TZ", "QX", "QY", "PX", "PY")
+# F: Miller accumulator ((F00,F01,F02),(F10,F11,F12)) shared by the K pairs of a group; per pair j: T (projective point),
+# Q (affine G2 input), PX = (xP, 0), PY = (yP, 0); G: second Fp12 operand of the product tree (aliases temporaries)
+
+
+def state_names(k):
+    return [n for h in FSLOTS for n in h] + ["%s%d" % (n, j) for j in range(k) for n in PAIR_STATE] + [n for h in GSLOTS for n in h]
 
 
 def get_f(b, names=FSLOTS): return tuple(tuple(b.inp(n) for n in h) for h in names)
-def get_t(b): return (b.inp("TX"), b.inp("TY"), b.inp("TZ"))
+def get_t(b, j): return (b.inp("TX%d" % j), b.inp("TY%d" % j), b.inp("TZ%d" % j))
 
 
 def put_f(b, f, names=FSLOTS):
@@ -279,44 +290,70 @@ def put_f(b, f, names=FSLOTS):
             b.out(n, v)
 
 
-def put_t(b, T):
-    for v, n in zip(T, ("TX", "TY", "TZ")):
+def put_t(b, T, j):
+    for v, n in zip(T, ("TX%d" % j, "TY%d" % j, "TZ%d" % j)):
         b.out(n, v)
 
 
-def prog_dbl(cfg, first=False):
-    """T <- 2T, f <- f^2 * line (first: f == 1, so f <- line)."""
+def guard_line(b, line, j, k):
+    """K > 1: the line of a pair with a point at infinity becomes 1 (the pair contributes 1 to the shared accumulator)."""
+    if k == 1:
+        return line   # a lone pair is fixed up after the loop (f <- 1)
+    ly, lx, lc = line
+    # 1 = ly + 0 w + 0 w^3 (D-type) / lc + 0 w^2 + 0 w^3 (M-type): the constant term is ly on altbn128, lc on bls12-381
+    if b.cfg.is_bn:
+        return (b.sel1(ly, j), b.sel0(lx, j), b.sel0(lc, j))
+    return (b.sel0(ly, j), b.sel0(lx, j), b.sel1(lc, j))
+
+
+def prog_dbl(cfg, k=1, first=False):
+    """T_j <- 2 T_j, f <- f^2 * prod_j line_j (first: f == 1, so f <- prod_j line_j)."""
     b = Builder(cfg)
-    T, line = b.dbl_step(get_t(b), b.inp("PX"), b.inp("PY"))
-    put_t(b, T)
+    lines = []
+    for j in range(k):
+        T, line = b.dbl_step(get_t(b, j), b.inp("PX%d" % j), b.inp("PY%d" % j))
+        put_t(b, T, j)
+        lines.append(guard_line(b, line, j, k))
     if first:
-        f = b.line_as_f12(*line)
-        f = tuple(tuple(b.copy(x) for x in h) for h in f)
+        f = b.line_as_f12(*lines[0])
+        if k == 1:
+            f = tuple(tuple(b.copy(x) for x in h) for h in f)
+        rest = lines[1:]
     else:
-        f = b.f12_mul_line(b.f12_sqr(get_f(b)), *line)
+        f = b.f12_sqr(get_f(b))
+        rest = lines
+    for line in rest:
+        f = b.f12_mul_line(f, *line)
+    if first and k > 1:   # outputs must be operation results (constants cannot be state)
+        f = tuple(tuple(x if x.kind not in ("in", "const") else b.copy(x) for x in h) for h in f)
     put_f(b, f)
     return b
 
 
-def prog_add(cfg, neg=False, q=("QX", "QY")):
+def prog_add(cfg, k=1, neg=False):
     b = Builder(cfg)
-    Q = (b.inp(q[0]), b.inp("NQY" if neg else q[1]))
-    T, line = b.add_step(get_t(b), Q, b.inp("PX"), b.inp("PY"))
-    put_t(b, T)
-    put_f(b, b.f12_mul_line(get_f(b), *line))
+    f = get_f(b)
+    for j in range(k):
+        qy = b.inp("QY%d" % j)
+        Q = (b.inp("QX%d" % j), b.neg(qy) if neg else qy)
+        T, line = b.add_step(get_t(b, j), Q, b.inp("PX%d" % j), b.inp("PY%d" % j))
+        put_t(b, T, j)
+        f = b.f12_mul_line(f, *guard_line(b, line, j, k))
+    put_f(b, f)
     return b
 
 
-def prog_bn_frob(cfg, which):
+def prog_bn_frob(cfg, k, which):
     """which = 1: (QX, QY) <- Q1 = (conj(x) g2, conj(y) g3); which = 2: (QX, QY) <- -Q2 with Q2 = frobenius(Q1), i.e.
     (conj(x1) g2, -conj(y1) g3) -- pairing.cuh: miller_loop tail."""
     b = Builder(cfg)
-    x = b.mul(b.conj(b.inp("QX")), b.const("G12"))
-    y = b.mul(b.conj(b.inp("QY")), b.const("G13"))
-    if which == 2:
-        y = b.neg(y)
-    b.out("QX", x)
-    b.out("QY", y)
+    for j in range(k):
+        x = b.mul(b.conj(b.inp("QX%d" % j)), b.const("G12"))
+        y = b.mul(b.conj(b.inp("QY%d" % j)), b.const("G13"))
+        if which == 2:
+            y = b.neg(y)
+        b.out("QX%d" % j, x)
+        b.out("QY%d" % j, y)
     return b
 
 
@@ -324,12 +361,6 @@ def prog_conj(cfg):
     b = Builder(cfg)
     for n in FSLOTS[1]:
         b.out(n, b.neg(b.inp(n)))
-    return b
-
-
-def prog_negq(cfg):
-    b = Builder(cfg)
-    b.out("NQY", b.neg(b.inp("QY")))
     return b
 
 
@@ -489,7 +520,7 @@ def schedule(b: Builder, g: int, state_slots: dict, const_slots: dict, ntemp_bas
     def enc(v, as_mul=False):
         k = v.kind
         a = slot_of[id(v.a)] if v.a is not None else 0
-        bb = slot_of[id(v.b)] if v.b is not None else 0
+        bb = slot_of[id(v.b)] if v.b is not None else v.imm
         if as_mul:
             k, bb = MUL, a
         return (k, slot_of[id(v)], a, bb)
@@ -550,25 +581,24 @@ def check_hazards(rounds, g):
 
 # ------------------------------------------------------------------------------------------- whole engine description
 class Engine:
-    """All programs of one curve for one lane count, with a common slot map."""
+    """All programs of one curve for one group shape (g lanes per group of k pairs), with a common slot map."""
 
-    def __init__(self, cfg: Cfg, g: int, tries=1, slot_weight=0.0):
-        self.cfg, self.g = cfg, g
-        self.state = {n: i for i, n in enumerate(STATE[:14])}   # F, T, Q, PX, PY, NQY
-        ntemp = 14
+    def __init__(self, cfg: Cfg, g: int, k: int = 1, tries=1, slot_weight=0.0):
+        self.cfg, self.g, self.k = cfg, g, k
+        names = state_names(k)
+        nstate = 6 + 7 * k
+        self.state = {n: i for i, n in enumerate(names)}   # F, per-pair state, then G right after (fixed: the tree's copy-in code uses them)
+        pair_state = names[6:nstate]
+        gnames = names[nstate:]
         self.const_names = ["ZERO", "ONE"] + (["B2X3", "G12", "G13"] if cfg.is_bn else [])
         self.consts = {n: CONST0 + i for i, n in enumerate(self.const_names)}
-        # the G operand of the tree product lives in temporaries that the Miller programs use too: give it fixed slots
-        # right after the state so MUL12 and the copy-in code agree
-        for i, n in enumerate(STATE[14:]):
-            self.state[n] = ntemp + i
         self.progs = {}
-        ntemp_g = ntemp + 6
-        specs = [("DBL", lambda: prog_dbl(cfg), STATE[14:]), ("DBL1", lambda: prog_dbl(cfg, first=True), STATE[14:]),
-                 ("ADD", lambda: prog_add(cfg), STATE[14:]), ("CONJ", lambda: prog_conj(cfg), ()), ("MUL12", lambda: prog_mul12(cfg), STATE[6:14])]
+        ntemp_g = nstate + 6
+        specs = [("DBL", lambda: prog_dbl(cfg, k), gnames), ("DBL1", lambda: prog_dbl(cfg, k, first=True), gnames),
+                 ("ADD", lambda: prog_add(cfg, k), gnames), ("CONJ", lambda: prog_conj(cfg), ()), ("MUL12", lambda: prog_mul12(cfg), pair_state)]
         if cfg.is_bn:
-            specs += [("SUBQ", lambda: prog_add(cfg, neg=True), STATE[14:]), ("NEGQ", lambda: prog_negq(cfg), ()),
-                      ("FROB1", lambda: prog_bn_frob(cfg, 1), ()), ("FROB2", lambda: prog_bn_frob(cfg, 2), ())]
+            specs += [("SUBQ", lambda: prog_add(cfg, k, neg=True), gnames),
+                      ("FROB1", lambda: prog_bn_frob(cfg, k, 1), ()), ("FROB2", lambda: prog_bn_frob(cfg, k, 2), ())]
         self.nslots = ntemp_g
         import random
         for name, mk, alias in specs:
@@ -595,8 +625,6 @@ class Engine:
         cfg = self.cfg
         digits = cfg.loop_naf if (use_naf and cfg.is_bn) else cfg.loop_bin
         seq = []
-        if cfg.is_bn and use_naf:
-            seq.append("NEGQ")
         for i, d in enumerate(digits):
             seq.append("DBL1" if i == 0 else "DBL")
             if d == 1:
@@ -617,6 +645,7 @@ class Emu:
         self.eng = eng
         self.F = eng.cfg.F
         self.slots = {}
+        self.flags = 0       # bit j: sub-pair j of the group has a point at infinity
         for s, v in zip(range(CONST0, CONST0 + len(eng.const_names)), eng.const_values()):
             self.slots[s] = v
 
@@ -653,20 +682,30 @@ class Emu:
                     v = (-x[0] % p, -x[1] % p)
                 elif k == COPY:
                     v = x
+                elif k in (SEL0, SEL1):
+                    v = ((1, 0) if k == SEL1 else (0, 0)) if (self.flags >> b) & 1 else x
                 else:
                     raise ValueError(k)
                 res.append((d, v))
             for d, v in res:
                 self.slots[d] = v
 
-    def miller(self, P, Q, use_naf=True):
-        """P = (x, y) ints, Q = ((x0, x1), (y0, y1)); returns f as [w^0..w^5] Fp2 coefficients."""
+    def miller(self, Ps, Qs, use_naf=True):
+        """Ps[j] = (x, y) ints or None (infinity), Qs[j] = ((x0, x1), (y0, y1)) or None, j < K; returns the shared
+        accumulator f = prod_j f_j as [w^0..w^5] Fp2 coefficients (K = 1: the caller replaces f by 1 for an infinity pair)."""
+        if self.eng.k == 1 and not isinstance(Ps, list):
+            Ps, Qs = [Ps], [Qs]
         for n in FSLOTS[0] + FSLOTS[1]:
             self.set(n, (0, 0))
         self.set("F00", (1, 0))
-        self.set("TX", Q[0]); self.set("TY", Q[1]); self.set("TZ", (1, 0))
-        self.set("QX", Q[0]); self.set("QY", Q[1])
-        self.set("PX", (P[0], 0)); self.set("PY", (P[1], 0))
+        self.flags = 0
+        for j, (P, Q) in enumerate(zip(Ps, Qs)):
+            if P is None or Q is None:
+                self.flags |= 1 << j
+                P, Q = (0, 0), ((0, 0), (0, 0))
+            self.set("TX%d" % j, Q[0]); self.set("TY%d" % j, Q[1]); self.set("TZ%d" % j, (1, 0))
+            self.set("QX%d" % j, Q[0]); self.set("QY%d" % j, Q[1])
+            self.set("PX%d" % j, (P[0], 0)); self.set("PY%d" % j, (P[1], 0))
         for name in self.eng.sequence(use_naf):
             self.run(name)
         c0 = [self.get(n) for n in FSLOTS[0]]
@@ -683,14 +722,14 @@ def emit(path):
     out = ["// GENERATED by tools/gen_slotvm.py -- do not edit.", "// Programs and constants of the slot engine (slotvm.cuh).",
            "#pragma once", "#include <cstdint>", "namespace bgls { namespace svt {"]
     for cfg in (BN, BLS):
-        for g in LANES:
-            eng = engine(cfg, g)
-            tag = "%s_G%d" % (cfg.cname, g)
+        for g, kk in SHAPES:
+            eng = engine(cfg, g, kk)
+            tag = "%s_G%d" % (cfg.cname, g) + ("K%d" % kk if kk > 1 else "")
             seq = eng.sequence(True)
             names = list(eng.progs)
             out.append("struct %s {" % tag)
-            out.append("    static constexpr int G = %d, NSLOT = %d, NCONST = %d, NPROG = %d, SEQ_LEN = %d;" %
-                       (g, eng.nslots, len(eng.const_names), len(names), len(seq)))
+            out.append("    static constexpr int G = %d, K = %d, NSLOT = %d, NCONST = %d, NPROG = %d, SEQ_LEN = %d;" %
+                       (g, kk, eng.nslots, len(eng.const_names), len(names), len(seq)))
             for n, s in eng.state.items():
                 out.append("    static constexpr int S_%s = %d;" % (n, s))
             for i, n in enumerate(names):
@@ -713,6 +752,10 @@ def emit(path):
                     cw += words32(c * cfg.R % cfg.p, cfg.N)
             out.append("    static const uint32_t* consts() { static const uint32_t v[%d] = {%s}; return v; }" %
                        (len(cw), ", ".join("0x%08xu" % w for w in cw)))
+            ml = 10 if cfg.is_bn else 14   # limbs of the machine's 28-bit form (tools/gen_machine.py)
+            out.append("    static constexpr int MACH_L = %d;" % ml)
+            out.append("    static const uint32_t* mach_r() { static const uint32_t v[%d] = {%s}; return v; }" %
+                       (cfg.N, ", ".join("0x%08xu" % w for w in words32(pow(2, 28 * ml, cfg.p), cfg.N))))
             out.append("};")
             st = {n: eng.progs[n].stats() for n in names}
             out.append("// %s: slots %d; %s" % (tag, eng.nslots, "; ".join("%s %d rounds (%d heavy ops, %d light, %d mixed)" % (
@@ -723,14 +766,16 @@ def emit(path):
 
 
 LANES = (1, 2, 4)
+SHAPES = ((1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (8, 2), (4, 2))   # (lanes per group, pairs per group)
 _ENGINES = {}
 
 
-def engine(cfg, g):
-    """The released engine description of (curve, lanes per pair): schedule search with a mild preference for fewer slots."""
-    key = (cfg.name, g)
+def engine(cfg, g, k=1):
+    """The released engine description of (curve, lanes per group, pairs per group): schedule search with a mild
+    preference for fewer slots."""
+    key = (cfg.name, g, k)
     if key not in _ENGINES:
-        _ENGINES[key] = Engine(cfg, g, tries=120, slot_weight=4.0)
+        _ENGINES[key] = Engine(cfg, g, k, tries=120, slot_weight=4.0)
     return _ENGINES[key]
 
 
@@ -738,6 +783,6 @@ if __name__ == "__main__":
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     emit(os.path.join(root, "bgls_b200", "csrc", "slotvm_tables.cuh"))
     for cfg in (BN, BLS):
-        for g in LANES:
-            eng = engine(cfg, g)
-            print(cfg.name, "G =", g, "slots", eng.nslots, {n: s.stats() for n, s in eng.progs.items()}, file=sys.stderr)
+        for g, kk in SHAPES:
+            eng = engine(cfg, g, kk)
+            print(cfg.name, "G =", g, "K =", kk, "slots", eng.nslots, {n: s.stats() for n, s in eng.progs.items()}, file=sys.stderr)
