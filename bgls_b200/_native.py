@@ -22,7 +22,7 @@ EXPORTS = [
     "bgls_compress_points", "bgls_compress_points_dev", "bgls_decompress_points", "bgls_decompress_points_dev",
     "bgls_verify_aggregate_signature", "bgls_verify_multi_signature",
     "bgls_exchange_create", "bgls_exchange_connect", "bgls_exchange_error", "bgls_miller_product_exchange_dev",
-    "bgls_final_exp_exchanged_dev",
+    "bgls_final_exp_exchanged_dev", "bgls_validate_points", "bgls_validate_points_dev", "bgls_gt_pow",
 ]
 
 _lib = None
@@ -74,6 +74,9 @@ def load():
     L.bgls_exchange_error.argtypes = [vp, ip]
     L.bgls_miller_product_exchange_dev.argtypes = [vp, i, vp, vp, sz, i, ctypes.c_uint64, vp]
     L.bgls_final_exp_exchanged_dev.argtypes = [vp, i, i, ctypes.c_uint64, vp, vp, vp]
+    L.bgls_validate_points.argtypes = [vp, i, i, cp, sz, i, cp]
+    L.bgls_validate_points_dev.argtypes = [vp, i, i, vp, sz, i, vp, vp]
+    L.bgls_gt_pow.argtypes = [vp, i, cp, cp, i, cp]
     L.bgls_launch_count.argtypes = [vp]
     L.bgls_launch_count.restype = ctypes.c_uint64
     L.bgls_set_profiling.argtypes = [vp, i]
@@ -175,12 +178,30 @@ class Context:
         self._chk(self._L.bgls_verify_multi_signature(self._h, curve, msg, len(msg), keys, n, sig, ctypes.byref(ok)))
         return bool(ok.value)
 
+    def verify_multi_signature_ptr(self, curve, msg: bytes, h_keys: int, n: int, sig: bytes) -> bool:
+        """Same call with the keys at a raw host address (pinned buffer of the bench)."""
+        ok = ctypes.c_int(0)
+        self._chk(self._L.bgls_verify_multi_signature(self._h, curve, msg, len(msg), ctypes.c_char_p(h_keys), n, sig, ctypes.byref(ok)))
+        return bool(ok.value)
+
     def verify_aggregate_signature_ptr(self, curve, h_msgs: int, h_offsets: int, n: int, h_keys: int, h_sig: int, allow_duplicates: bool = False) -> bool:
         """Same call on raw host pointers (pinned buffers of the bench)."""
         ok = ctypes.c_int(0)
         self._chk(self._L.bgls_verify_aggregate_signature(self._h, curve, ctypes.c_char_p(h_msgs), ctypes.cast(h_offsets, ctypes.POINTER(ctypes.c_uint64)),
                                                           n, ctypes.c_char_p(h_keys), ctypes.c_char_p(h_sig), 1 if allow_duplicates else 0, ctypes.byref(ok)))
         return bool(ok.value)
+
+    def validate_points(self, curve, group, pts: bytes, n: int, reference: bool = True) -> list:
+        """What the reference checks when it builds a Point (bgls_validate_points): list of n booleans."""
+        ok = ctypes.create_string_buffer(max(n, 1))
+        self._chk(self._L.bgls_validate_points(self._h, curve, group, pts, n, 1 if reference else 0, ok))
+        return [b != 0 for b in ok.raw[:n]]
+
+    def gt_pow(self, curve, a: bytes, e: int) -> bytes:
+        """PointT.Mul: a^e in GT."""
+        out = ctypes.create_string_buffer(12 * FP_BYTES[curve])
+        self._chk(self._L.bgls_gt_pow(self._h, curve, a, abs(e).to_bytes(32, "big"), 1 if e < 0 else 0, out))
+        return out.raw
 
     def compress_points(self, curve, group, pts: bytes, n: int) -> bytes:
         """n uncompressed records -> n compressed records (Point.Marshal)."""

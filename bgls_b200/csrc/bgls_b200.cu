@@ -346,6 +346,11 @@ __global__ void __launch_bounds__(32) k_exchange_wait(const unsigned long long* 
     __threadfence_system();
 }
 
+// a wait that timed out must not leave a verdict computed from stale mailbox records behind
+__global__ void k_exchange_guard(const int* __restrict__ err, int* __restrict__ is_identity) {
+    if (*err && is_identity) *is_identity = 0;
+}
+
 // compressed wire formats, one point per thread (codec.cuh)
 template <class C, int G>
 __global__ void __launch_bounds__(TB) k_compress(const uint8_t* __restrict__ pts, size_t n, uint8_t* __restrict__ out) {
@@ -365,6 +370,18 @@ __global__ void __launch_bounds__(TB) k_decompress(const uint8_t* __restrict__ i
     if (G == 1) good = decompress_g1<C>(pts + i * 2 * F, in + i * F, check_subgroup != 0);
     else good = decompress_g2<C>(pts + i * 4 * F, in + i * 2 * F, check_subgroup != 0);
     ok[i] = good ? 1 : 0;
+}
+
+template <class C, int G>
+__global__ void __launch_bounds__(TB) k_validate(const uint8_t* __restrict__ pts, size_t n, int subgroup, uint8_t* __restrict__ ok) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    constexpr int F = C::FP_BYTES;
+    ok[i] = (G == 1 ? validate_g1<C>(pts + i * 2 * F, subgroup != 0) : validate_g2<C>(pts + i * 4 * F, subgroup != 0)) ? 1 : 0;
+}
+template <class C>
+__global__ void __launch_bounds__(32) k_gt_pow(const uint8_t* __restrict__ a, const uint8_t* __restrict__ e32, int negative, uint8_t* __restrict__ out) {
+    if (threadIdx.x == 0) gt_pow<C>(out, a, e32, negative != 0);
 }
 
 // register-only IMAD.WIDE.U32 loop: the integer-pipe roofline denominator.  The multiplier operand is
@@ -531,11 +548,11 @@ size_t agg_work_bytes(int curve, int group, size_t n) {
 }
 template <class C>
 int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final, uint8_t* d_out,
-                    int* d_flag, void* work, cudaStream_t s) {
+                    int* d_flag, void* work, cudaStream_t s, bool prof) {
     const int nb = blocks_for(n);
     int nb_used = nb;
     Fp12<C>* partial = (Fp12<C>*)work;
-    if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
+    if (prof) cudaEventRecord(ctx->ev[0], s);
     if (n >= MSHARED_MIN && !ctx->no_shared) {
         const int nbs = blocks_for((n + MSHARE - 1) / MSHARE);
         k_miller_product_shared<C, MSHARE><<<nbs, TB, 0, s>>>(d_g1, d_g2, n, partial);
@@ -545,10 +562,10 @@ int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, siz
         k_miller_product<C><<<nb, TB, 0, s>>>(d_g1, d_g2, n, partial);
         ctx->launches++;
     }
-    if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
+    if (prof) cudaEventRecord(ctx->ev[1], s);
     k_finish<C, false><<<1, TB, 0, s>>>(partial, n > 0 ? (size_t)nb_used : 0, do_final, d_out, d_flag);
     ctx->launches++;
-    if (ctx->profiling) cudaEventRecord(ctx->ev[2], s);
+    if (prof) cudaEventRecord(ctx->ev[2], s);
     CU(cudaGetLastError());
     return BGLS_OK;
 }
@@ -580,10 +597,10 @@ int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, cons
               void* d_ok, void* work, cudaStream_t s);
 
 int pairing_dev_thread(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
-                void* d_flag, void* work, cudaStream_t s) {
+                void* d_flag, void* work, cudaStream_t s, bool prof) {
     if (curve == BGLS_ALTBN128)
-        return enqueue_pairing<BN254>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
-    return enqueue_pairing<BLS381>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+        return enqueue_pairing<BN254>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s, prof);
+    return enqueue_pairing<BLS381>(ctx, (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s, prof);
 }
 int finish_bytes_dev_thread(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, cudaStream_t s) {
     if (curve == BGLS_ALTBN128) k_finish<BN254, true><<<1, TB, 0, s>>>(d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag);
@@ -923,7 +940,7 @@ size_t mach_work_for(int curve, size_t n) {
 }
 int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
                 void* d_flag, void* work, cudaStream_t s) {
-    if (ctx->thread_engine) return pairing_dev_thread(ctx, curve, d_g1, d_g2, n, do_final, d_out, d_flag, work, s);
+    if (ctx->thread_engine) return pairing_dev_thread(ctx, curve, d_g1, d_g2, n, do_final, d_out, d_flag, work, s, ctx->profiling);
     if (use_slot_engine(ctx, n)) {
         // throughput regime: Miller loops and product tree on the slot engine (saturated limbs, 8 lanes per group of 2 pairs
         // that share their accumulator), then the machine's final exponentiation in its low-footprint form
@@ -942,10 +959,7 @@ int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, si
         uint8_t* raw = tw + align_up((size_t)blocks_for(n) * fp12_dev_bytes(curve));
         uint8_t* mw = raw + align_up(12 * F);
         if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
-        const bool prof = ctx->profiling;
-        ctx->profiling = false;
-        int rc = pairing_dev_thread(ctx, curve, d_g1, d_g2, n, 0, raw, nullptr, tw, s);
-        ctx->profiling = prof;
+        int rc = pairing_dev_thread(ctx, curve, d_g1, d_g2, n, 0, raw, nullptr, tw, s, false);   // no shared state is toggled
         if (rc) return rc;
         if (ctx->profiling) cudaEventRecord(ctx->ev[1], s);
         rc = finish_bytes_dev(ctx, curve, raw, 1, do_final, d_out, d_flag, mw, s);
@@ -1154,7 +1168,17 @@ void bgls_ctx_destroy(bgls_ctx* ctx) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
 }
-const char* bgls_last_error(const bgls_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* bgls_last_error(const bgls_ctx* ctx) {
+    if (!ctx) return "null context";
+    // a copy per calling thread, taken under the lock: the pointer stays valid (until this thread asks again) while other
+    // threads fail and overwrite the context's text
+    static thread_local std::string copy;
+    {
+        std::lock_guard<std::mutex> lk(const_cast<bgls_ctx*>(ctx)->err_mu);
+        copy = ctx->err;
+    }
+    return copy.c_str();
+}
 uint64_t bgls_launch_count(const bgls_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int bgls_set_profiling(bgls_ctx* ctx, int on) {
@@ -1388,6 +1412,67 @@ int bgls_decompress_points_dev(bgls_ctx* ctx, int curve, int group, const void* 
     CU(cudaSetDevice(ctx->device));
     return codec_dev(ctx, curve, group, false, d_in, n, check_subgroup, d_out_pts, d_out_ok, (cudaStream_t)stream);
 }
+static int validate_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, int mode, void* d_ok, cudaStream_t s) {
+    if (n == 0) return BGLS_OK;
+    const unsigned nb = (unsigned)((n + TB - 1) / TB);
+    const uint8_t* in = (const uint8_t*)d_pts;
+    uint8_t* ok = (uint8_t*)d_ok;
+    const int sub = mode == BGLS_VALIDATE_REFERENCE ? 1 : 0;
+    if (curve == BGLS_ALTBN128) {
+        if (group == 1) k_validate<BN254, 1><<<nb, TB, 0, s>>>(in, n, sub, ok);
+        else k_validate<BN254, 2><<<nb, TB, 0, s>>>(in, n, sub, ok);
+    } else {
+        if (group == 1) k_validate<BLS381, 1><<<nb, TB, 0, s>>>(in, n, sub, ok);
+        else k_validate<BLS381, 2><<<nb, TB, 0, s>>>(in, n, sub, ok);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+int bgls_validate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, int mode, uint8_t* out_ok) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (mode != BGLS_VALIDATE_ONCURVE && mode != BGLS_VALIDATE_REFERENCE) ||
+        (n && (!pts || !out_ok)))
+        return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    if (n == 0) return BGLS_OK;
+    SlotLock sl(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t rec = 2 * group * fp_bytes(curve), bi = align_up(n * rec), bk = align_up(n);
+    int rc = ensure_scratch(ctx, sl.s, bi + bk);
+    if (rc) return rc;
+    uint8_t *din = (uint8_t*)sl.s->scratch, *dok = din + bi;
+    CU(cudaMemcpyAsync(din, pts, n * rec, cudaMemcpyHostToDevice, sl.s->stream));
+    rc = validate_dev(ctx, curve, group, din, n, mode, dok, sl.s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_ok, dok, n, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
+    return BGLS_OK;
+}
+int bgls_validate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, int mode, void* d_out_ok, void* stream) {
+    if (!ctx || !curve_ok(curve) || (group != 1 && group != 2) || (mode != BGLS_VALIDATE_ONCURVE && mode != BGLS_VALIDATE_REFERENCE) ||
+        (n && (!d_pts || !d_out_ok)))
+        return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    return validate_dev(ctx, curve, group, d_pts, n, mode, d_out_ok, (cudaStream_t)stream);
+}
+int bgls_gt_pow(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* exponent32, int negative, uint8_t* out_gt) {
+    if (!ctx || !curve_ok(curve) || !a || !exponent32 || !out_gt) return fail(ctx, BGLS_ERR_ARG, "bad argument");
+    SlotLock sl(ctx);
+    CU(cudaSetDevice(ctx->device));
+    const size_t F = fp_bytes(curve), bi = align_up(12 * F), be = align_up(32);
+    int rc = ensure_scratch(ctx, sl.s, 2 * bi + be);
+    if (rc) return rc;
+    uint8_t *da = (uint8_t*)sl.s->scratch, *de = da + bi, *dout = de + be;
+    CU(cudaMemcpyAsync(da, a, 12 * F, cudaMemcpyHostToDevice, sl.s->stream));
+    CU(cudaMemcpyAsync(de, exponent32, 32, cudaMemcpyHostToDevice, sl.s->stream));
+    if (curve == BGLS_ALTBN128) k_gt_pow<BN254><<<1, 32, 0, sl.s->stream>>>(da, de, negative, dout);
+    else k_gt_pow<BLS381><<<1, 32, 0, sl.s->stream>>>(da, de, negative, dout);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sl.s->hres, dout, 12 * F, cudaMemcpyDeviceToHost, sl.s->stream));
+    CU(cudaStreamSynchronize(sl.s->stream));
+    memcpy(out_gt, sl.s->hres, 12 * F);
+    return BGLS_OK;
+}
 static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_off, size_t n, void* d_out, cudaStream_t s) {
     if (n == 0) return BGLS_OK;
     if (curve == BGLS_ALTBN128)
@@ -1595,10 +1680,12 @@ struct PeerPtrs {
     uint8_t* slot[8];
     unsigned long long* flag[8];
 };
+// records of one (lane, parity) are contiguous with the curve's own record size (the finishing side reads them as one
+// array of `world` wire records); every (lane, parity) group starts on a multiple of XREC * world bytes
 static size_t xch_rec_off(const Exchange& x, int lane, int parity, int r, size_t rec) {
-    return ((size_t)(lane * 2 + parity) * x.world + r) * rec;
+    return (size_t)(lane * 2 + parity) * x.world * XREC + (size_t)r * rec;
 }
-static size_t xch_flag_base(const Exchange& x) { return align_up((size_t)x.lanes * 2 * x.world * 576, 256); }
+static size_t xch_flag_base(const Exchange& x) { return align_up((size_t)x.lanes * 2 * x.world * XREC, 256); }
 static size_t xch_flag_off(const Exchange& x, int lane, int parity, int r) {
     return xch_flag_base(x) + ((size_t)(lane * 2 + parity) * x.world + r) * sizeof(unsigned long long);
 }
@@ -1643,6 +1730,7 @@ int bgls_exchange_error(bgls_ctx* ctx, int* err) {
     if (!ctx || !err || !ctx->xch.d_err) return fail(ctx, BGLS_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpy(err, ctx->xch.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*err) CU(cudaMemset(ctx->xch.d_err, 0, sizeof(int)));   // reported once: a timeout does not poison later epochs
     return BGLS_OK;
 }
 int bgls_miller_product_exchange_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int lane,
@@ -1685,7 +1773,12 @@ int bgls_final_exp_exchanged_dev(bgls_ctx* ctx, int curve, int lane, uint64_t ep
     k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)(x.local + xch_flag_off(x, lane, parity, 0)), x.world,
                                                          (unsigned long long)epoch, x.d_err);
     ctx->launches++;
-    return finish_bytes_dev(ctx, curve, x.local + xch_rec_off(x, lane, parity, 0, rec), x.world, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
+    rc = finish_bytes_dev(ctx, curve, x.local + xch_rec_off(x, lane, parity, 0, rec), x.world, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
+    if (rc) return rc;
+    k_exchange_guard<<<1, 1, 0, (cudaStream_t)stream>>>(x.d_err, (int*)d_is_identity);   // timed-out wait -> verdict false
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BGLS_OK;
 }
 int bgls_final_exp_product_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, void* d_out_gt,
                                void* d_is_identity, void* stream) {

@@ -208,4 +208,82 @@ template <class C> HDNI bool decompress_g2(uint8_t* rec, const uint8_t* in, bool
     return true;
 }
 
+// ---------------------------------------------------------------- validation of uncompressed records
+// What the reference enforces when a Point is built from coordinates or bytes (the engine's kernels assume it):
+//   altbn128  bn256.G1/G2.Unmarshal (curves/altbn128.go:42-57,160-179,296-376): coordinates < q, on the curve, and for G2
+//             membership in the order-r subgroup (the library's twist-point check multiplies by the order)
+//   bls12-381 Unmarshal + Check() (curves/bls12_381.go:242-264), MakeG*Point(check = true) (:197-226): on the curve and in
+//             the order-r subgroup
+// subgroup = false checks range and curve equation only.  Infinity records are valid.
+template <class C> HDNI bool validate_g1(const uint8_t* rec, bool subgroup) {
+    constexpr int F = C::FP_BYTES;
+    if (!C::IS_BN && (rec[0] & 0x40)) {   // bls12 infinity flag: everything else must be zero
+        uint32_t x = rec[0] & 0xBF;
+        for (int i = 1; i < 2 * F; i++) x |= rec[i];
+        return x == 0;
+    }
+    if (bytes_all_zero(rec, 2 * F)) return true;
+    if (!be_below_p<C>(rec) || !be_below_p<C>(rec + F)) return false;
+    Fp<C> x, y, y2, chk;
+    fp_from_be<C>(x, rec);
+    fp_from_be<C>(y, rec + F);
+    g1_y2<C>(y2, x);
+    fp_sqr(chk, y);
+    if (!fp_eq(chk, y2)) return false;
+    if (subgroup && !C::IS_BN) {   // altbn128 G1 has cofactor 1
+        Jac<Fp<C>> p, q;
+        p.X = x; p.Y = y; p.inf = false;
+        fe_one(p.Z);
+        jac_mul(q, p, order_be<C>());
+        if (!(q.inf || fe_is_zero(q.Z))) return false;
+    }
+    return true;
+}
+template <class C> HDNI bool validate_g2(const uint8_t* rec, bool subgroup) {
+    constexpr int F = C::FP_BYTES;
+    if (!C::IS_BN && (rec[0] & 0x40)) {
+        uint32_t x = rec[0] & 0xBF;
+        for (int i = 1; i < 4 * F; i++) x |= rec[i];
+        return x == 0;
+    }
+    if (bytes_all_zero(rec, 4 * F)) return true;
+    for (int k = 0; k < 4; k++)
+        if (!be_below_p<C>(rec + k * F)) return false;
+    Fp2<C> x, y, y2, chk;
+    fp_from_be<C>(x.c1, rec);
+    fp_from_be<C>(x.c0, rec + F);
+    fp_from_be<C>(y.c1, rec + 2 * F);
+    fp_from_be<C>(y.c0, rec + 3 * F);
+    g2_y2<C>(y2, x);
+    fp2_sqr(chk, y);
+    if (!fp2_eq(chk, y2)) return false;
+    if (subgroup) {
+        Jac<Fp2<C>> p, q;
+        p.X = x; p.Y = y; p.inf = false;
+        fe_one(p.Z);
+        jac_mul(q, p, order_be<C>());
+        if (!(q.inf || fe_is_zero(q.Z))) return false;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- GT exponentiation (PointT.Mul)
+// out = a^e for a in GT (unitary: the cyclotomic squaring applies; the inverse is the conjugate), e = 32-byte big-endian
+// magnitude with a sign -- curves/altbn128.go:290-294 (ScalarMult), curves/bls12_381.go:186-195.
+template <class C> HDNI void gt_pow(uint8_t* out, const uint8_t* a_be, const uint8_t* e32, bool negative) {
+    Fp12<C> a, acc;
+    fp12_from_be<C>(a, a_be);
+    if (negative) fp12_conj(a, a);
+    fp12_one(acc);
+    bool started = false;
+    for (int i = 0; i < 256; i++) {
+        if (started) fp12_cyc_sqr(acc, acc);
+        if ((e32[i >> 3] >> (7 - (i & 7))) & 1) {
+            if (started) fp12_mul(acc, acc, a);
+            else { acc = a; started = true; }
+        }
+    }
+    fp12_to_be<C>(out, acc);
+}
+
 }  // namespace bgls

@@ -125,7 +125,11 @@ class PointT:
         return self.raw
 
     def Mul(self, scalar):
-        raise NotImplementedError("GT exponentiation is not on the accelerated path")
+        """GT exponentiation (curves/altbn128.go:290-294; bls12_381.go:186-195) on the engine (bgls_gt_pow)."""
+        e = int(scalar)
+        if abs(e) >> 256:
+            e %= self.curve.order      # GT has order r
+        return PointT(self.curve, self.curve._ctx().gt_pow(self.curve.cid, self.raw, e))
 
 
 class CurveSystem:
@@ -146,15 +150,26 @@ class CurveSystem:
         return self.name
 
     # ---- constructors
+    def _validated(self, group, raw, always):
+        """The checks the reference makes before a Point exists (bgls_validate_points, mode REFERENCE): altbn128 builds
+        every point through bn256.Unmarshal (on the curve; G2 also in the order-r subgroup; `check` is ignored,
+        curves/altbn128.go:39-57,160-179), bls12-381 calls Check() when asked to (curves/bls12_381.go:197-226) and on every
+        Unmarshal (:242-264)."""
+        if always and not self._ctx().validate_points(self.cid, group, raw, 1, reference=True)[0]:
+            return None, False
+        return Point(self, group, raw), True
+
     def MakeG1Point(self, coords, check=True):
         if len(coords) != 2 or any(not (0 <= int(c) < self.q) for c in coords):
             return None, False
-        return Point(self, 1, b"".join(int(c).to_bytes(self.fp_bytes, "big") for c in coords)), True
+        raw = b"".join(int(c).to_bytes(self.fp_bytes, "big") for c in coords)
+        return self._validated(1, raw, self.cid == ALTBN128 or check)
 
     def MakeG2Point(self, coords, check=True):
         if len(coords) != 4 or any(not (0 <= int(c) < self.q) for c in coords):
             return None, False
-        return Point(self, 2, b"".join(int(c).to_bytes(self.fp_bytes, "big") for c in coords)), True
+        raw = b"".join(int(c).to_bytes(self.fp_bytes, "big") for c in coords)
+        return self._validated(2, raw, self.cid == ALTBN128 or check)
 
     def _unmarshal(self, group, data):
         """curves/altbn128.go:296-376, bls12_381.go:242-264: uncompressed or compressed by length; the compressed form
@@ -164,10 +179,11 @@ class CurveSystem:
             return None, False
         data = bytes(data)
         if len(data) == 2 * group * F:
-            return Point(self, group, data), True
+            return self._validated(group, data, True)
         if len(data) != group * F:
             return None, False
-        raw, ok = self._ctx().decompress_points(self.cid, group, data, 1, check_subgroup=(self.cid == BLS12_381))
+        # subgroup membership: bls12-381 Check(), and the upstream twist check of altbn128 G2
+        raw, ok = self._ctx().decompress_points(self.cid, group, data, 1, check_subgroup=(self.cid == BLS12_381 or group == 2))
         return (Point(self, group, raw), True) if ok[0] else (None, False)
 
     def UnmarshalG1(self, data):

@@ -160,7 +160,7 @@ class PointT {
     PointT Copy() const { return *this; }
     bool Equals(const PointT& o) const { return !nil() && !o.nil() && o.curve_ == curve_ && raw_ == o.raw_; }
     Bytes Marshal() const { return raw_; }
-    PointT Mul(const Int&) const { throw std::logic_error("GT exponentiation is not on the accelerated path"); }
+    PointT Mul(const Int& scalar) const;   // GT exponentiation (altbn128.go:290-294; bls12_381.go:186-195): bgls_gt_pow
 
   private:
     const CurveSystem* curve_ = nullptr;
@@ -249,7 +249,18 @@ class CurveSystem {
     bool Is(const Point& p, int group) const { return !p.nil() && p.curve() == this && p.group() == group; }
 
   private:
-    std::pair<Point, bool> Make(int group, const std::vector<Bytes>& coords, bool) const {
+    // the checks the reference makes before a Point exists (bgls_validate_points, mode REFERENCE): altbn128 builds every
+    // point through bn256.Unmarshal (on the curve, G2 also in the order-r subgroup; `check` is ignored, altbn128.go:39-57,
+    // 160-179); bls12-381 calls Check() when asked to (bls12_381.go:197-226) and on every Unmarshal (:242-264)
+    std::pair<Point, bool> Validated(int group, const Bytes& raw, bool always) const {
+        if (always) {
+            uint8_t ok = 0;
+            Engine::Check(ctx(), bgls_validate_points(ctx(), cid_, group, raw.data(), 1, BGLS_VALIDATE_REFERENCE, &ok), "validate");
+            if (!ok) return {Point(), false};
+        }
+        return {Point(this, group, raw), true};
+    }
+    std::pair<Point, bool> Make(int group, const std::vector<Bytes>& coords, bool check) const {
         if (coords.size() != (size_t)2 * group) return {Point(), false};
         Bytes raw;
         for (auto& c : coords) {
@@ -259,16 +270,17 @@ class CurveSystem {
             if (detail::cmp_be(v.data(), q_.data(), F_) >= 0) return {Point(), false};
             raw.insert(raw.end(), v.begin(), v.end());
         }
-        return {Point(this, group, raw), true};
+        return Validated(group, raw, cid_ == BGLS_ALTBN128 || check);
     }
     // altbn128.go:296-376, bls12_381.go:242-264: uncompressed or compressed by length; the compressed form is decoded
     // on the GPU (bls12-381 with the subgroup check the reference's Check() performs)
     std::pair<Point, bool> Unmarshal(int group, const Bytes& data) const {
-        if (data.size() == 2 * group * F_) return {Point(this, group, data), true};
+        if (data.size() == 2 * group * F_) return Validated(group, data, true);
         if (data.size() != group * F_) return {Point(), false};
         Bytes raw(2 * group * F_);
         uint8_t ok = 0;
-        Engine::Check(ctx(), bgls_decompress_points(ctx(), cid_, group, data.data(), 1, cid_ == BGLS_BLS12_381, raw.data(), &ok), "Unmarshal");
+        // subgroup membership: bls12-381 Check(), and the upstream twist check of altbn128 G2
+        Engine::Check(ctx(), bgls_decompress_points(ctx(), cid_, group, data.data(), 1, cid_ == BGLS_BLS12_381 || group == 2, raw.data(), &ok), "Unmarshal");
         if (!ok) return {Point(), false};
         return {Point(this, group, raw), true};
     }
@@ -327,6 +339,13 @@ inline std::pair<PointT, bool> PointT::Add(const PointT& o) const {
     Bytes out(raw_.size());
     Engine::Check(curve_->ctx(), bgls_gt_mul(curve_->ctx(), curve_->id(), raw_.data(), o.raw_.data(), out.data()), "PointT.Add");
     return {PointT(curve_, out), true};
+}
+
+inline PointT PointT::Mul(const Int& scalar) const {
+    if (nil()) throw std::logic_error("Mul on a nil PointT");
+    Bytes out(raw_.size());
+    Engine::Check(curve_->ctx(), bgls_gt_pow(curve_->ctx(), curve_->id(), raw_.data(), scalar.mag.data(), scalar.neg ? 1 : 0, out.data()), "PointT.Mul");
+    return PointT(curve_, out);
 }
 
 // curves/curve.go:73-110.  One engine call for the whole list (the reference's goroutine tree computes the same group

@@ -15,9 +15,11 @@
  *              (the cloudflare bn256 gfP12 marshal order, curves/altbn128.go:378-380)
  *     The point at infinity is the all-zero record (curves/README.md:19); for bls12-381 a record
  *     whose first byte has bit 0x40 set is also accepted as infinity.  Outputs always use zeros.
- *   - inputs must be on-curve, reduced (< p) coordinates: the reference rejects anything else when
- *     the Point is constructed (curves/altbn128.go:50-55,172-177), before this boundary.
- *     No subgroup check is made, as in the reference.
+ *   - the arithmetic entry points assume valid points: reduced (< p) coordinates on the curve (and, where the
+ *     reference enforces it, in the order-r subgroup).  The reference rejects anything else when the Point is
+ *     constructed (curves/altbn128.go:42-57,160-179; curves/bls12_381.go:197-226,242-264), i.e. before this boundary;
+ *     a binding does the same with bgls_validate_points (uncompressed records) / bgls_decompress_points (compressed)
+ *     when it builds a Point from untrusted coordinates or bytes.  Verdicts on invalid points are undefined.
  *   - every function returns BGLS_OK (0) or a negative error; the Go side maps non-zero to
  *     `ok == false` / `nil` (curves/curve.go:126-128,137-139).  bgls_last_error() gives the text.
  *   - host-buffer entry points copy in, run on the context's stream and synchronise before
@@ -25,10 +27,12 @@
  *     (as void*), enqueue the work and return without synchronising.
  *   - a context is bound to one CUDA device and is safe to share between threads / goroutines (the
  *     reference calls Pair / PairingProduct from many goroutines, curves/curve.go:132-134).  It owns
- *     24 execution slots (stream + device scratch each): concurrent host-buffer calls run on different
+ *     64 execution slots (stream + device scratch each): concurrent host-buffer calls run on different
  *     slots and overlap on the GPU -- the single-warp final exponentiation of one product beside the
  *     Miller loops of the next.  `_dev` calls are keyed by the caller's stream: work enqueued on
- *     different streams uses different scratch; more than 24 streams in flight are serialised.
+ *     different streams uses different scratch; more than 64 streams in flight are serialised.
+ *     The first call of a given size on a slot allocates its scratch and SYNCHRONISES the device (also for `_dev`
+ *     calls; not legal inside a stream capture: warm the context up with a call of the largest size first).
  *     bgls_last_error() returns the text of the most recent failing call on the context.
  */
 #ifndef BGLS_B200_H
@@ -170,6 +174,21 @@ int bgls_verify_multi_signature(bgls_ctx* ctx, int curve, const uint8_t* msg, si
  *   0x20 larger root) -- restated from the format's definition, the upstream source is not in the reference tree. */
 int bgls_compress_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out);
 int bgls_compress_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, void* d_out, void* stream);
+
+/* Validation of uncompressed records -- what CurveSystem.MakeG1Point / MakeG2Point / UnmarshalG1 / UnmarshalG2 enforce
+ * before a Point exists (curves/altbn128.go:42-57,160-179; curves/bls12_381.go:197-226,242-264).
+ * out_ok[i] = 1 when record i is the point at infinity or has coordinates < q that satisfy the curve equation and
+ *   BGLS_VALIDATE_ONCURVE    nothing more (bls12-381 MakeG*Point with check = false does not even do this)
+ *   BGLS_VALIDATE_REFERENCE  what the reference's decoding enforces: additionally r*P = infinity for altbn128 G2 (the
+ *                            upstream bn256 twist check) and for bls12-381 G1 / G2 (Check()); altbn128 G1 has cofactor 1. */
+#define BGLS_VALIDATE_ONCURVE 0
+#define BGLS_VALIDATE_REFERENCE 1
+int bgls_validate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, int mode, uint8_t* out_ok);
+int bgls_validate_points_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t n, int mode, void* d_out_ok, void* stream);
+
+/* PointT.Mul -- curves/curve.go:63-70; curves/altbn128.go:290-294; curves/bls12_381.go:186-195.
+ * out_gt = a^e for a GT element a; exponent32 = |e| as 32 big-endian bytes, negative != 0 for e < 0 (a^-1 is the conjugate). */
+int bgls_gt_pow(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* exponent32, int negative, uint8_t* out_gt);
 
 /* CurveSystem.UnmarshalG1 / UnmarshalG2 on compressed input -- curves/altbn128.go:296-376 (square roots
  * curves/hash.go:178-223); curves/bls12_381.go:242-264.  out_pts: n uncompressed records (zeros where rejected);

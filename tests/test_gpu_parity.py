@@ -444,3 +444,81 @@ def test_peer_memory_exchange_single_rank(cid, c):
         assert ctx2.exchange_error() == 0
     finally:
         ctx2.close()
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_validate_points_rejects_what_the_reference_rejects(ctx, cid, c):
+    """MakeG1Point / MakeG2Point / Unmarshal semantics (curves/altbn128.go:42-57,160-179; bls12_381.go:197-226,242-264):
+    off-curve, unreduced (>= q) and out-of-subgroup records are refused before a Point exists."""
+    from bgls_b200.curves import Altbn128, Bls12
+    crv = Altbn128 if cid == 0 else Bls12
+    nb, p = c.nbytes, c.p
+    be = lambda v: int(v).to_bytes(nb, "big")
+    rng = random.Random(90 + cid)
+    good1, _ = rand_points(cid, c, 1, 3, rng)
+    good2, _ = rand_points(cid, c, 2, 3, rng)
+    # G1: valid points, infinity, off-curve (y + 1), unreduced x + q (does not fit for bls12: x + q < 2^384 always fits)
+    P = c.unmarshal_g1(good1[:2 * nb])
+    recs1 = [good1[:2 * nb], bytes(2 * nb), be(P[0]) + be((P[1] + 1) % p), be(P[0] + p if (P[0] + p).bit_length() <= 8 * nb else p) + be(P[1])]
+    exp1 = [True, True, False, False]
+    # a point on the curve outside the order-r subgroup (bls12 G1 has a cofactor; altbn128 G1 does not)
+    if cid == 1:
+        x = 5
+        while True:
+            y2 = (x ** 3 + c.b) % p
+            y = pow(y2, (p + 1) // 4, p)
+            if y * y % p == y2 and c.g1_mul((x, y), c.r) is not None:
+                break
+            x += 1
+        recs1.append(be(x) + be(y))
+        exp1.append(False)
+    assert ctx.validate_points(cid, 1, b"".join(recs1), len(recs1)) == exp1
+    assert ctx.validate_points(cid, 1, b"".join(recs1), len(recs1), reference=False) == exp1[:4] + [True] * (len(exp1) - 4)
+    # G2: valid, infinity, off-curve, and a twist point outside the subgroup (both curves have a G2 cofactor)
+    Q = c.unmarshal_g2(good2[:4 * nb])
+    bad_y = c.marshal_g2((Q[0], ((Q[1][0] + 1) % p, Q[1][1])))
+    F2 = c.F2
+    xr = (3, 1)
+    while True:
+        y2 = F2.add(F2.mul(xr, F2.mul(xr, xr)), c.b2)
+        yr = c.sqrt_fp2(y2)
+        if F2.mul(yr, yr) == y2 and c.g2_mul((xr, yr), c.r) is not None:
+            break
+        xr = (xr[0] + 1, xr[1])
+    recs2 = [good2[:4 * nb], bytes(4 * nb), bad_y, c.marshal_g2((xr, yr))]
+    assert ctx.validate_points(cid, 2, b"".join(recs2), 4) == [True, True, False, False]
+    assert ctx.validate_points(cid, 2, b"".join(recs2), 4, reference=False) == [True, True, False, True]
+    # the host mirror applies them where the reference does
+    pt, ok = crv.MakeG1Point([P[0], (P[1] + 1) % p], check=True)
+    assert pt is None and not ok
+    pt, ok = crv.MakeG1Point([P[0], P[1]], check=True)
+    assert ok and pt.raw == good1[:2 * nb]
+    pt, ok = crv.UnmarshalG2(recs2[3])
+    assert pt is None and not ok
+    pt, ok = crv.UnmarshalG2(recs2[2])
+    assert pt is None and not ok
+    pt, ok = crv.UnmarshalG1(recs1[2])
+    assert pt is None and not ok
+    pt, ok = crv.UnmarshalG2(good2[:4 * nb])
+    assert ok
+    if cid == 1:   # bls12-381 MakeG*Point(check = false) skips Check() (bls12_381.go:203,222)
+        pt, ok = crv.MakeG1Point([P[0], (P[1] + 1) % p], check=False)
+        assert ok
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_gt_pow_is_point_t_mul(ctx, cid, c):
+    """PointT.Mul (curves/curve.go:63-70): e(P, Q)^k == e(kP, Q); k = 0, 1, -1, r-1 and random."""
+    from bgls_b200.curves import Altbn128, Bls12
+    crv = Altbn128 if cid == 0 else Bls12
+    rng = random.Random(17 + cid)
+    g1, ks = rand_points(cid, c, 1, 1, rng)
+    g2, _ = rand_points(cid, c, 2, 1, rng)
+    base = ctx.pair(cid, c.marshal_g1(c.g1), g2)
+    assert ctx.gt_pow(cid, base, ks[0]) == ctx.pair(cid, g1, g2)
+    one = c.marshal_gt(c.fp12_one)
+    assert ctx.gt_pow(cid, base, 0) == one and ctx.gt_pow(cid, base, 1) == base
+    inv = ctx.gt_pow(cid, base, -1)
+    assert ctx.gt_mul(cid, inv, base) == one and ctx.gt_pow(cid, base, c.r - 1) == inv
+    t = crv.UnmarshalGT(base)[0]
+    assert t.Mul(ks[0]).Marshal() == ctx.pair(cid, g1, g2)

@@ -120,3 +120,63 @@ def test_batch_shared_accumulator_ragged(ctx):
         expect.append(good)
     assert offsets[-1] >= 8192
     assert ctx.pairing_check_batch(cid, b"".join(G1), b"".join(G2), offsets) == expect
+
+
+def _engine_ctx(name):
+    import os
+
+    import bgls_b200
+    old = os.environ.get("BGLS_ENGINE")
+    os.environ["BGLS_ENGINE"] = name
+    try:
+        return bgls_b200.Context(0)
+    finally:
+        if old is None:
+            del os.environ["BGLS_ENGINE"]
+        else:
+            os.environ["BGLS_ENGINE"] = old
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_large_rejecting_product_bytes_on_every_engine(ctx, cid, c):
+    """GT bytes of a REJECTING 40,001-pair product against the C oracle (shared final exponentiation, a second or two on
+    the host cores), on the default path (slot engine at this size) and on the thread engine's shared-accumulator kernel
+    (k_miller_product_shared, >= 32,768 pairs) -- and of a 4,000-pair product on all four engine settings."""
+    g1, g2 = synth_aggregate(ctx, cid, c, 2000, 11 + cid)
+    nb = c.nbytes
+    # 20 tiles of the 2,000 signer pairs + the (-sigma, g2) pair once: a product that is NOT the identity
+    big1, big2, n = g1[:2 * nb * 2000] * 20 + g1[2 * nb * 2000:], g2[:4 * nb * 2000] * 20 + g2[4 * nb * 2000:], 40001
+    want = C.pairing_product(cid, big1, big2, n, 16, 0)
+    assert want != c.marshal_gt(c.fp12_one)
+    gt, ok = ctx.pairing_product(cid, big1, big2, n)
+    assert gt == want and not ok
+    small1, small2, m = g1[:2 * nb * 2000] * 2, g2[:4 * nb * 2000] * 2, 4000
+    want_small = C.pairing_product(cid, small1, small2, m, 16, 0)
+    assert ctx.pairing_product(cid, small1, small2, m)[0] == want_small
+    for name in ("thread", "machine", "slot"):
+        e = _engine_ctx(name)
+        try:
+            assert e.pairing_product(cid, small1, small2, m)[0] == want_small, name
+            if name != "machine":   # (the machine at 40,001 pairs is covered by the property tests above)
+                gt, ok = e.pairing_product(cid, big1, big2, n)
+                assert gt == want and not ok, name
+        finally:
+            e.close()
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_batch_path_verdicts_against_oracle(ctx, cid, c):
+    """Config-5 shape at reduced count: 40 checks x 257 pairs (the throughput batch path: >= 8,192 pairs in total), some
+    corrupted; every verdict must be the oracle's for that check's own product."""
+    g1, g2 = synth_aggregate(ctx, cid, c, 256, 23 + cid)
+    nb = c.nbytes
+    bad1 = g1[2 * nb:4 * nb] + g1[:2 * nb] + g1[4 * nb:]          # two messages swapped
+    bad2 = g2[:4 * nb * 5] + g2[4 * nb * 6:4 * nb * 7] + g2[4 * nb * 6:]   # a key replaced by its neighbour
+    variants = [(g1, g2), (bad1, g2), (g1, bad2)]
+    exp = [C.pairing_product(cid, a, b, 257, 16, 0) == c.marshal_gt(c.fp12_one) for a, b in variants]
+    assert exp == [True, False, False]
+    order = [0, 1, 0, 0, 2, 0, 1, 0] * 5
+    all1 = b"".join(variants[k][0] for k in order)
+    all2 = b"".join(variants[k][1] for k in order)
+    offs = [257 * i for i in range(len(order) + 1)]
+    assert ctx.pairing_check_batch(cid, all1, all2, offs) == [exp[k] for k in order]
