@@ -909,14 +909,45 @@ int slot_pairing(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const u
     if (rc) return rc;
     uint32_t* levels = (uint32_t*)work;
     uint32_t* mval = (uint32_t*)((char*)levels + align_up((sv_tree_words(nb, SLOT_FANIN, C::N) + 1) * 4));
-    MachFinishArgs fa{md.f, do_final ? md.finalexp : md.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN, d_out, d_flag};
+    MachFinishArgs fa{md.f, do_final ? md.finalexp : md.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN, d_out, d_flag, nullptr};
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
-    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, n, levels, tl_slot->tickets, mval, T::MACH_L, fa, ctx->trace);
+    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, n, levels, tl_slot->tickets, mval, T::MACH_L, fa, SvBatch{}, ctx->trace);
     ctx->launches++;
     if (ctx->profiling) { cudaEventRecord(ctx->ev[1], s); cudaEventRecord(ctx->ev[2], s); }
     CU(cudaGetLastError());
     return BGLS_OK;
 }
+// nbatch independent products in one launch (k_slot_plan + k_slot_miller in batch form): verdict bytes in d_ok
+size_t slot_batch_blocks(size_t nbatch, size_t total) { return total / SLOT_PAIRS_PER_BLOCK + nbatch; }   // upper bound
+size_t slot_batch_work_bytes(int curve, size_t nbatch, size_t total) {
+    const size_t N = curve == BGLS_ALTBN128 ? 8 : 12, L = curve == BGLS_ALTBN128 ? 10 : 14, nb = slot_batch_blocks(nbatch, total);
+    return 3 * align_up((nbatch + 1) * 4) + align_up((nb + nb / 4 + 8 * nbatch) * 12 * N * 4) + align_up(nbatch * 12 * L * 4);
+}
+template <class C, class T, class F>
+int slot_batch(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const uint8_t* d_g1, const uint8_t* d_g2, const unsigned long long* d_off,
+               size_t nbatch, size_t total, uint8_t* d_ok, void* work, cudaStream_t s) {
+    using FIN = MachFinisher<F>;
+    constexpr int NPB = SLOT_WPB * 32 / T::G;
+    constexpr size_t smem = std::max(sv_smem_bytes<C, T, NPB>(), FIN::SMEM_BYTES);
+    if (!tl_slot) return fail(ctx, BGLS_ERR_ARG, "slot engine called outside an execution slot");
+    const size_t nb = slot_batch_blocks(nbatch, total);
+    int rc = ensure_tickets(ctx, tl_slot, nb / 4 + 8 * nbatch + 8);   // >= sum of sv_tree_counters over the products
+    if (rc) return rc;
+    char* w = (char*)work;
+    unsigned* bstart = (unsigned*)w;
+    unsigned* lstart = (unsigned*)(w + align_up((nbatch + 1) * 4));
+    unsigned* tstart = (unsigned*)(w + 2 * align_up((nbatch + 1) * 4));
+    uint32_t* levels = (uint32_t*)(w + 3 * align_up((nbatch + 1) * 4));
+    uint32_t* mvals = (uint32_t*)((char*)levels + align_up((nb + nb / 4 + 8 * nbatch) * 12 * C::N * 4));
+    k_slot_plan<<<1, 1024, 0, s>>>(d_off, nbatch, (unsigned)SLOT_PAIRS_PER_BLOCK, (unsigned)SLOT_FANIN, bstart, lstart, tstart);
+    MachFinishArgs fa{md.f, md.finalexp, F::FINALEXP_LEN, nullptr, nullptr, nullptr};
+    SvBatch b{d_off, bstart, lstart, tstart, nbatch, d_ok};
+    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, 0, levels, tl_slot->tickets, mvals, T::MACH_L, fa, b, ctx->trace);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+
 // load estimate: pairing calls inside the library (host-buffer entry points) or recently enqueued (device-resident ones)
 long long now_us() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 int busy_estimate(bgls_ctx* ctx) {
@@ -976,9 +1007,17 @@ int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k,
         return mach_finish_bytes<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
     return mach_finish_bytes<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
 }
+constexpr size_t SLOT_BATCH_MIN_PAIRS = 2048;   // total pairs from which a batch fills the GPU with the slot engine
 int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
               void* d_ok, void* work, cudaStream_t s) {
     if (ctx->thread_engine) return batch_dev_thread(ctx, curve, d_g1, d_g2, d_off, nbatch, total, d_ok, work, s);
+    if (nbatch && (ctx->engine == ENGINE_SLOT || (ctx->engine == ENGINE_AUTO && total >= SLOT_BATCH_MIN_PAIRS))) {
+        if (curve == BGLS_ALTBN128)
+            return slot_batch<BN254, SlotBN, mtab::BN254_F>(ctx, ctx->sloteng[0], ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2,
+                                                            (const unsigned long long*)d_off, nbatch, total, (uint8_t*)d_ok, work, s);
+        return slot_batch<BLS381, SlotBLS, mtab::BLS381_F>(ctx, ctx->sloteng[1], ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2,
+                                                            (const unsigned long long*)d_off, nbatch, total, (uint8_t*)d_ok, work, s);
+    }
     if (curve == BGLS_ALTBN128)
         return mach_batch<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2, (const unsigned long long*)d_off, nbatch, total, (uint8_t*)d_ok, work, s);
     return mach_batch<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2, (const unsigned long long*)d_off, nbatch, total, (uint8_t*)d_ok, work, s);
@@ -1633,7 +1672,7 @@ int bgls_pairing_check_batch(bgls_ctx* ctx, int curve, const uint8_t* g1, const 
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(total * 2 * F), b2 = align_up(total * 4 * F);
     const size_t bf = align_up((nbatch + 1) * 8), bk = align_up(nbatch);
-    const size_t bw = std::max(align_up(total * fp12_dev_bytes(curve)), mach_work_for(curve, total + nbatch));
+    const size_t bw = std::max({align_up(total * fp12_dev_bytes(curve)), mach_work_for(curve, total + nbatch), slot_batch_work_bytes(curve, nbatch, total)});
     int rc = ensure_scratch(ctx, sl.s, b1 + b2 + bf + bk + bw);
     if (rc) return rc;
     uint8_t *d1 = (uint8_t*)sl.s->scratch, *d2 = d1 + b1, *doff = d2 + b2, *dok = doff + bf, *work = dok + bk;
@@ -1811,7 +1850,7 @@ int bgls_pairing_check_batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, con
     SlotLock sl(ctx, (cudaStream_t)stream);
     CU(cudaSetDevice(ctx->device));
     void* work;
-    int rc = dev_work(ctx, sl.s, std::max(align_up(total_pairs * fp12_dev_bytes(curve)), mach_work_for(curve, total_pairs + nbatch)), &work);
+    int rc = dev_work(ctx, sl.s, std::max({align_up(total_pairs * fp12_dev_bytes(curve)), mach_work_for(curve, total_pairs + nbatch), slot_batch_work_bytes(curve, nbatch, total_pairs)}), &work);
     if (rc) return rc;
     return batch_dev(ctx, curve, d_g1, d_g2, d_offsets, nbatch, total_pairs, d_out_ok, work, (cudaStream_t)stream);
 }

@@ -350,6 +350,7 @@ struct MachFinishArgs {
     int plen;
     uint8_t* out_gt;      // 12 F bytes (may be null)
     int* flag32;          // is-identity flag (may be null)
+    uint8_t* flag8;       // is-identity flag, byte form (batches; may be null)
 };
 // one warp; `sm`: at least F::NS * F::L words of shared memory; `in`: the value in machine form ([12][L] limbs)
 template <class F>
@@ -389,12 +390,19 @@ __device__ __forceinline__ void mach_finish_warp(uint32_t* sm, const MachFinishA
     }
     const unsigned okb = __ballot_sync(0xFFFFFFFFu, ok);
     if (gl == 0 && a.flag32) *a.flag32 = (okb & 0xFFFu) == 0xFFFu;
+    if (gl == 0 && a.flag8) *a.flag8 = (uint8_t)((okb & 0xFFFu) == 0xFFFu);
 }
 template <class F> struct MachFinisher {   // tail of k_slot_miller (slotvm.cuh)
     using Args = MachFinishArgs;
     static constexpr size_t SMEM_BYTES = (size_t)F::NS * F::L * sizeof(uint32_t);
     static constexpr int MACH_L = F::L;
     __device__ __forceinline__ static void run(uint32_t* sm, const Args& a, const uint32_t* in) { mach_finish_warp<F>(sm, a, in); }
+    __device__ __forceinline__ static Args for_product(Args a, uint8_t* flags8, size_t c) {   // product c of a batch
+        a.out_gt = nullptr;
+        a.flag32 = nullptr;
+        a.flag8 = flags8 + c;
+        return a;
+    }
 };
 template <class F>
 __global__ void __launch_bounds__(32) k_mach_finish_lean(MachFinishArgs a, const uint32_t* __restrict__ in) {

@@ -282,14 +282,89 @@ struct SvNoFinish {
     struct Args { int unused; };
     static constexpr size_t SMEM_BYTES = 0;
     __device__ __forceinline__ static void run(uint32_t*, const Args&, const uint32_t*) {}
+    __device__ __forceinline__ static Args for_product(const Args& a, uint8_t*, size_t) { return a; }
 };
+// Batch of independent products in one launch (throughput mode, BASELINE config 5): product c covers the pairs
+// [off[c], off[c+1]).  k_slot_plan lays the blocks, tree levels and tickets of every product out (prefix sums); block b of
+// k_slot_miller then finds its product by binary search.  batch.nbatch == 0: one product over all n pairs.
+struct SvBatch {
+    const unsigned long long* off;   // nbatch + 1 pair offsets (device)
+    const unsigned* bstart;          // nbatch + 1: first block of every product
+    const unsigned* lstart;          // nbatch + 1: first tree-level value of every product
+    const unsigned* tstart;          // nbatch + 1: first ticket of every product
+    size_t nbatch;
+    uint8_t* flags8;                 // nbatch verdicts (1 = the product is the identity)
+};
+__device__ __forceinline__ unsigned sv_tree_values_dev(unsigned nb, unsigned fan) {
+    unsigned w = 0;
+    for (unsigned c = nb; c > 1; c = (c + fan - 1) / fan) w += c;
+    return w;
+}
+__device__ __forceinline__ unsigned sv_tree_tickets_dev(unsigned nb, unsigned fan) {
+    unsigned k = 0;
+    for (unsigned c = nb; c > 1; c = (c + fan - 1) / fan) k += (c + fan - 1) / fan;
+    return k;
+}
+// one block: exclusive prefix sums over the products (chunked over the threads, then combined)
+__global__ void __launch_bounds__(1024) k_slot_plan(const unsigned long long* __restrict__ off, size_t nbatch, unsigned pairs_per_block, unsigned fan,
+                                                    unsigned* __restrict__ bstart, unsigned* __restrict__ lstart, unsigned* __restrict__ tstart) {
+    __shared__ unsigned sb[1024], sl[1024], st[1024];
+    const size_t chunk = (nbatch + blockDim.x - 1) / blockDim.x;
+    const size_t lo = (size_t)threadIdx.x * chunk, hi = lo + chunk < nbatch ? lo + chunk : nbatch;
+    unsigned b = 0, l = 0, t = 0;
+    for (size_t c = lo; c < hi; c++) {
+        const unsigned nb = (unsigned)((off[c + 1] - off[c] + pairs_per_block - 1) / pairs_per_block);
+        const unsigned nbe = nb ? nb : 1;   // an empty product still gets one block (it writes the verdict of the empty product)
+        b += nbe; l += sv_tree_values_dev(nbe, fan); t += sv_tree_tickets_dev(nbe, fan);
+    }
+    sb[threadIdx.x] = b; sl[threadIdx.x] = l; st[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ab = 0, al = 0, at = 0;
+        for (unsigned i = 0; i < blockDim.x; i++) {
+            const unsigned xb = sb[i], xl = sl[i], xt = st[i];
+            sb[i] = ab; sl[i] = al; st[i] = at;
+            ab += xb; al += xl; at += xt;
+        }
+        bstart[nbatch] = ab; lstart[nbatch] = al; tstart[nbatch] = at;
+    }
+    __syncthreads();
+    b = sb[threadIdx.x]; l = sl[threadIdx.x]; t = st[threadIdx.x];
+    for (size_t c = lo; c < hi; c++) {
+        bstart[c] = b; lstart[c] = l; tstart[c] = t;
+        const unsigned nb = (unsigned)((off[c + 1] - off[c] + pairs_per_block - 1) / pairs_per_block);
+        const unsigned nbe = nb ? nb : 1;
+        b += nbe; l += sv_tree_values_dev(nbe, fan); t += sv_tree_tickets_dev(nbe, fan);
+    }
+}
+
 template <class C, class T, int WPB, class FIN>
 __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                           size_t n, uint32_t* __restrict__ partials, unsigned* __restrict__ counters,
                                                           uint32_t* __restrict__ mach_out, int mach_l, typename FIN::Args fin,
-                                                          unsigned long long* __restrict__ trace) {
+                                                          SvBatch batch, unsigned long long* __restrict__ trace) {
     constexpr int N = C::N, FB = C::FP_BYTES, G = T::G, K = T::K, NPB = WPB * 32 / G, W4 = 2 * N / 4;
     extern __shared__ uint4 sv_sm[];
+    // ---- which product, which block of it
+    size_t blk = blockIdx.x, nblk = gridDim.x, pair0 = 0;
+    if (batch.nbatch) {
+        if (blockIdx.x >= batch.bstart[batch.nbatch]) return;
+        size_t lo = 0, hi = batch.nbatch;            // last c with bstart[c] <= blockIdx.x
+        while (hi - lo > 1) {
+            const size_t mid = (lo + hi) / 2;
+            if (batch.bstart[mid] <= blockIdx.x) lo = mid; else hi = mid;
+        }
+        blk = blockIdx.x - batch.bstart[lo];
+        nblk = batch.bstart[lo + 1] - batch.bstart[lo];
+        pair0 = batch.off[lo];
+        n = batch.off[lo + 1] - pair0;
+        g1 += pair0 * 2 * FB;
+        g2 += pair0 * 4 * FB;
+        partials += (size_t)batch.lstart[lo] * 12 * N;
+        counters += batch.tstart[lo];
+        mach_out += lo * 12 * (mach_l ? mach_l : N);
+        fin = FIN::for_product(fin, batch.flags8, lo);
+    }
     unsigned long long t_start = 0;
     if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     // the program words stay in global memory: a few KB read by every warp of the GPU, i.e. L1 hits; staging them per
@@ -304,8 +379,8 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int q = (threadIdx.x >> 5) * GPW + lane % GPW, gl = lane / GPW;
-    const size_t first = (size_t)blockIdx.x * NPB * K;                  // first pair of the block
-    const size_t ngroups_left = (n - first + K - 1) / K;
+    const size_t first = blk * NPB * K;                                 // first pair of the block (relative to its product)
+    const size_t ngroups_left = n > first ? (n - first + K - 1) / K : 0;
     const int ngroups = (int)(ngroups_left < (size_t)NPB ? ngroups_left : (size_t)NPB);
     SlotFile<C, NPB> sf{slots, consts, q, 0};
     // ---- inputs: G1 = x || y, G2 = x_im || x_re || y_im || y_re (big-endian); coordinate c of pair j is converted by lane
@@ -345,6 +420,7 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
         sv_run<C, NPB, G>(slots, consts, q, inf, code, tb.offs[pid], tb.offs[pid + 1], gl, true);
     }
     if (K == 1 && inf && gl == 0) sv_set_one<C, T, NPB>(sf);            // K > 1: the lines of such pairs were replaced by 1
+    // (a block without pairs -- the empty product -- still ran the programs on all-infinity groups: group 0 holds 1)
     sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, ngroups);
     if (trace && threadIdx.x == 0) {   // BGLS_TRACE: (start ns, end ns, SM) of every Miller block, for timeline reconstruction
         unsigned long long t_end;
@@ -361,7 +437,7 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
     // (measured: 2.6 M pairings/s with three tree launches per product, 4.1 M without them).
     constexpr int FAN = 2 * NPB;
     __shared__ int s_last;
-    size_t count = gridDim.x, idx = blockIdx.x;
+    size_t count = nblk, idx = blk;
     uint32_t* lvl = partials;
     unsigned* cnt = counters;
 #pragma unroll 1
@@ -407,40 +483,6 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
     }
 }
 
-// One level of the product tree over Fp12 values in the internal form: every block multiplies up to 2 * NPB values into one.
-template <class C, class T, int WPB>
-__global__ void __launch_bounds__(WPB * 32) k_slot_reduce(SvTables tb, const uint32_t* __restrict__ in, size_t m, uint32_t* __restrict__ out,
-                                                          int mach_l) {
-    constexpr int N = C::N, G = T::G, NPB = WPB * 32 / G, W4 = 2 * N / 4;
-    extern __shared__ uint4 sv_sm[];
-    SvU4* consts = (SvU4*)sv_sm;
-    SvU4* slots = consts + T::NCONST * W4;
-    for (int i = threadIdx.x; i < T::NCONST * 2 * N; i += blockDim.x) ((uint32_t*)consts)[i] = tb.consts[i];
-    constexpr int GPW = 32 / G;
-    const int lane = threadIdx.x & 31;
-    const int q = (threadIdx.x >> 5) * GPW + lane % GPW, gl = lane / GPW;
-    const size_t first = (size_t)blockIdx.x * 2 * NPB;
-    const size_t left = m - first;
-    const int nvals = (int)(left < (size_t)(2 * NPB) ? left : (size_t)(2 * NPB));
-    const int ngroups = (nvals + 1) / 2;
-    const SlotFile<C, NPB> sf{slots, consts, q, 0};
-    // group q: F <- value 2q, G <- value 2q + 1
-    for (int t = gl; t < 24; t += G) {
-        const int which = t / 12, idx = t % 12;   // which value, which Fp of it
-        const int v = 2 * q + which;
-        if (v < nvals) {
-            LN<N> x;
-            const uint32_t* src = in + (first + v) * 12 * N + idx * N;
-#pragma unroll
-            for (int i = 0; i < N; i++) x.v[i] = src[i];
-            sf.store_fp((which ? T::S_G00 : T::S_F00) + (idx >> 1), idx & 1, x);
-        }
-    }
-    __syncthreads();
-    sv_run<C, NPB, G>(slots, consts, q, 0, tb.code, tb.offs[T::P_MUL12], tb.offs[T::P_MUL12 + 1], gl, 2 * q + 1 < nvals);
-    sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, ngroups);
-    sv_emit_value<C, T, NPB>(slots, consts, tb, out + (size_t)blockIdx.x * 12 * (mach_l ? mach_l : N), mach_l);
-}
 #endif
 
 }  // namespace bgls

@@ -92,3 +92,31 @@ def test_auto_engine_switches_under_load(cid, c):
         t.join()
     assert not errs
     ctx.close()
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_slot_batch_ragged(sctx, cid, c):
+    """Batch mode of the slot engine (one launch for all products: plan kernel, per-product trees and final
+    exponentiations): ragged products -- empty, 1 pair, one block, several blocks -- with valid and rejecting ones mixed;
+    every verdict is the oracle's."""
+    rng = random.Random(555 + cid)
+    nb = c.nbytes
+    sizes = [0, 1, 2, 8, 9, 40, 0, 17, 64, 65, 3]
+    g1s, g2s, exp = [], [], []
+    for i, n in enumerate(sizes):
+        if n == 0:
+            g1, g2 = b"", b""
+        elif n == 1:
+            g1, g2 = c.marshal_g1(c.g1), c.marshal_g2(c.g2)
+        else:
+            g1, g2 = make_aggregate(cid, c, n - 1, rng, nthreads=8)
+            if i % 3 == 0:   # corrupt: swap two G1 points
+                g1 = g1[2 * nb:4 * nb] + g1[:2 * nb] + g1[4 * nb:]
+        g1s.append(g1)
+        g2s.append(g2)
+        exp.append(True if n == 0 else C.pairing_product(cid, g1, g2, n, 8, 0) == c.marshal_gt(c.fp12_one))
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    assert sctx.pairing_check_batch(cid, b"".join(g1s), b"".join(g2s), offs) == exp
+    assert any(exp) and not all(exp)
