@@ -24,6 +24,7 @@
 #include "pairing.cuh"
 #include "machine_kernels.cuh"
 #include "slotvm.cuh"
+#include "agg.cuh"
 #include "hash.cuh"
 #include "codec.cuh"
 
@@ -297,6 +298,44 @@ __global__ void __launch_bounds__(TB) k_hash_to_g1_bn(const uint8_t* __restrict_
         if (__all_sync(0xFFFFFFFFu, done)) break;
     }
 }
+// altbn128, throughput form: a warp owns 32 messages and deals its lanes out again every round -- lane L tries counter
+// next[m] + L / u of the (L mod u)-th unfinished message m, u = messages still open.  Round 1 is one counter per message
+// (half succeed), round 2 two counters for each of the ~16 left, round 3 eight for the ~4 left: ~3 square-root
+// exponentiations per message instead of the 8 of the latency form above.  The lowest successful counter of a message
+// wins, exactly what the sequential loop of hash.go:53-77 finds first.
+template <class C>
+__global__ void __launch_bounds__(TB) k_hash_to_g1_bn_pool(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
+                                                           uint8_t* __restrict__ out) {
+    static_assert(TB == 32, "one warp per block");
+    const int lane = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * 32;
+    bool done = base + lane >= n;
+    unsigned next = 0;                                   // next counter of this lane's own message
+    for (;;) {
+        const unsigned pending = __ballot_sync(0xFFFFFFFFu, !done);
+        if (!pending) break;
+        const int u = __popc(pending), per = 32 / u;     // `per` counters per open message this round
+        const int slot = lane % u, rep = lane / u;
+        const int owner = __fns(pending, 0, slot + 1);   // lane that owns the slot-th open message
+        const unsigned counter = __shfl_sync(0xFFFFFFFFu, next, owner) + rep;
+        const size_t i = base + owner;
+        const uint8_t* m = msgs + off[i];
+        const size_t len = (size_t)(off[i + 1] - off[i]);
+        Fp<C> px, root;
+        const bool ok = rep < per && counter < 256 && bn_hash_try<C>(px, root, (uint8_t)counter, m, len);
+        const unsigned hits = __ballot_sync(0xFFFFFFFFu, ok);
+        bool lower = false;                              // a smaller counter of the same message succeeded
+        for (int r = 0; r < rep; r++) lower |= (hits >> (slot + r * u)) & 1u;
+        if (ok && !lower) bn_hash_finish<C>(out + i * 2 * C::FP_BYTES, px, root, m, len);
+        if (!done) {
+            const int myslot = __popc(pending & ((1u << lane) - 1u));
+            bool any = false;
+            for (int r = 0; r < per; r++) any |= (hits >> (myslot + r * u)) & 1u;
+            if (any || next + per >= 256) done = true;   // 256 failures: probability 2^-256, the reference would spin
+            next += per;
+        }
+    }
+}
 template <class C>
 __global__ void __launch_bounds__(TB) k_hash_to_g1_bls(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
                                                        uint8_t* __restrict__ out) {
@@ -475,6 +514,8 @@ struct bgls_ctx {
     bool thread_engine = false;  // BGLS_ENGINE=thread: thread-per-pair kernels only
     bool machine_only = false;   // BGLS_ENGINE=machine: dot-product machine at every size (no hybrid)
     bool no_shared = false;      // BGLS_MILLER=noshare: thread engine without the shared Miller accumulator (one pair per thread)
+    int hash_mode = 0;           // BGLS_HASH=pool|wide: altbn128 try-and-increment form (0: by load)
+    int agg_blocks_per_sm = 0;   // BGLS_AGG_BLOCKS=k: at most k aggregation blocks per SM (0: as many as fit)
     int min_wpb = 8;             // BGLS_MIN_WPB=k: at least k pairings (warps) per block of k_mach_miller32
     bool miller16 = false;       // BGLS_MILLER=m16: 16-lane Miller program (two pairings per warp) instead of the pipelined one
     int device = 0;
@@ -543,8 +584,8 @@ size_t jac_dev_bytes(int c, int g) {
 
 // ---- enqueue helpers (device pointers); `work` is device scratch owned by the caller
 size_t agg_work_bytes(int curve, int group, size_t n) {
-    const size_t nb = (size_t)blocks_for(n);
-    return align_up((nb + nb / TB + 2) * jac_dev_bytes(curve, group));
+    const size_t nb = (n + 19) / 20 + 1, words = 3 * (size_t)group * (curve == BGLS_ALTBN128 ? 8 : 12);
+    return align_up((agg_tree_values(nb, 20) + 1) * words * 4);
 }
 template <class C>
 int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final, uint8_t* d_out,
@@ -569,22 +610,39 @@ int enqueue_pairing(bgls_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g2, siz
     CU(cudaGetLastError());
     return BGLS_OK;
 }
-template <class C, class F>
-int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, size_t rec, uint8_t* d_out, void* work, cudaStream_t s) {
-    const int nb = blocks_for(n);
-    Jac<F>* partial = (Jac<F>*)work;
-    Jac<F>* other = partial + nb;   // second buffer of the level tree (agg_work_bytes)
-    k_aggregate<C, F><<<nb, TB, 0, s>>>(d_pts, n, rec, partial);
-    ctx->launches++;
-    size_t k = (size_t)nb;
-    while (k > (size_t)TB) {   // log-depth tree over the block partials instead of one block walking all of them
-        const size_t nk = (k + TB - 1) / TB;
-        k_aggregate_level<F><<<(unsigned)nk, TB, 0, s>>>(partial, k, other);
-        ctx->launches++;
-        std::swap(partial, other);
-        k = nk;
+// AggregatePoints in one launch (agg.cuh): six lanes per addition, in-launch block and cross-block trees, one binary
+// inversion.  `work` = levels of the cross-block tree (agg_work_bytes); the tickets are the execution slot's.
+constexpr int AGG_WPB = 4, AGG_NGB = AGG_WPB * AGG_GPW;
+int ensure_tickets(bgls_ctx* ctx, Slot* sl, size_t count);
+thread_local Slot* tl_slot = nullptr;   // the execution slot of the API call running on this thread (set by SlotLock)
+template <class E> int agg_blocks_per_sm(bgls_ctx* ctx, int* out) {
+    static int cached = 0;
+    if (!cached) {
+        CU(cudaFuncSetAttribute(k_agg<E, AGG_WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem_bytes<E, AGG_NGB>()));
+        int b = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_agg<E, AGG_WPB>, AGG_WPB * 32, agg_smem_bytes<E, AGG_NGB>()));
+        cached = b > 0 ? b : 1;
     }
-    k_aggregate_finish<C, F><<<1, TB, 0, s>>>(partial, k, d_out);
+    *out = cached;
+    return BGLS_OK;
+}
+size_t agg_grid(size_t n, int sms, int per_sm) {
+    size_t nb = (n + AGG_NGB - 1) / AGG_NGB;
+    const size_t cap = (size_t)sms * per_sm;
+    if (nb > cap) nb = cap;
+    return nb ? nb : 1;
+}
+template <class E>
+int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, uint8_t* d_out, void* work, cudaStream_t s) {
+    if (!tl_slot) return fail(ctx, BGLS_ERR_ARG, "aggregation called outside an execution slot");
+    int per_sm = 1;
+    int rc = agg_blocks_per_sm<E>(ctx, &per_sm);
+    if (rc) return rc;
+    if (ctx->agg_blocks_per_sm > 0 && ctx->agg_blocks_per_sm < per_sm) per_sm = ctx->agg_blocks_per_sm;
+    const size_t nb = agg_grid(n, ctx->sms, per_sm);
+    rc = ensure_tickets(ctx, tl_slot, nb / AGG_NGB + 8);
+    if (rc) return rc;
+    k_agg<E, AGG_WPB><<<(unsigned)nb, AGG_WPB * 32, agg_smem_bytes<E, AGG_NGB>(), s>>>(d_pts, n, (uint32_t*)work, tl_slot->tickets, d_out, nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
     return BGLS_OK;
@@ -614,11 +672,11 @@ int aggregate_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, size_t
     const uint8_t* p = (const uint8_t*)d_pts;
     uint8_t* o = (uint8_t*)d_out;
     if (curve == BGLS_ALTBN128) {
-        if (group == 1) return enqueue_aggregate<BN254, Fp<BN254>>(ctx, p, n, rec, o, work, s);
-        return enqueue_aggregate<BN254, Fp2<BN254>>(ctx, p, n, rec, o, work, s);
+        if (group == 1) return enqueue_aggregate<AggFp<BN254>>(ctx, p, n, o, work, s);
+        return enqueue_aggregate<AggFp2<BN254>>(ctx, p, n, o, work, s);
     }
-    if (group == 1) return enqueue_aggregate<BLS381, Fp<BLS381>>(ctx, p, n, rec, o, work, s);
-    return enqueue_aggregate<BLS381, Fp2<BLS381>>(ctx, p, n, rec, o, work, s);
+    if (group == 1) return enqueue_aggregate<AggFp<BLS381>>(ctx, p, n, o, work, s);
+    return enqueue_aggregate<AggFp2<BLS381>>(ctx, p, n, o, work, s);
 }
 int scale_dev(bgls_ctx* ctx, int curve, int group, const void* d_pts, const void* d_sc, size_t n, void* d_out, cudaStream_t s) {
     const size_t rec = 2 * group * fp_bytes(curve);
@@ -880,7 +938,6 @@ size_t slot_work_bytes(int curve, size_t n) {
     return align_up((sv_tree_words(nb, SLOT_FANIN, N) + 1) * 4) + align_up(12 * L * 4);
 }
 // per-slot tickets of the in-launch product tree: zero between launches (the last arriver of a group resets its ticket)
-thread_local Slot* tl_slot = nullptr;   // the execution slot of the API call running on this thread (set by SlotLock)
 int ensure_tickets(bgls_ctx* ctx, Slot* sl, size_t count) {
     if (count <= sl->tickets_cap) return BGLS_OK;
     CU(cudaDeviceSynchronize());   // growth only (first call of a size): see ensure_scratch
@@ -1148,6 +1205,8 @@ int bgls_ctx_create(int device, bgls_ctx** out) {
     ctx->engine = ctx->thread_engine ? ENGINE_THREAD : ctx->machine_only ? ENGINE_MACHINE : (eng && std::string(eng) == "slot") ? ENGINE_SLOT : ENGINE_AUTO;
     const char* mil = getenv("BGLS_MILLER");
     ctx->miller16 = mil && std::string(mil) == "m16";
+    if (const char* hm = getenv("BGLS_HASH")) ctx->hash_mode = std::string(hm) == "pool" ? 1 : std::string(hm) == "wide" ? 2 : 0;
+    if (const char* ab = getenv("BGLS_AGG_BLOCKS")) ctx->agg_blocks_per_sm = atoi(ab);
     const char* mw = getenv("BGLS_MIN_WPB");
     if (mw && atoi(mw) > 0) ctx->min_wpb = atoi(mw);
     ctx->no_shared = mil && std::string(mil) == "noshare";
@@ -1267,14 +1326,15 @@ int bgls_intpipe_peak(bgls_ctx* ctx, double* wide_mac_per_s) {
 }
 
 // ---- host-buffer entry points
+struct Busy {   // load estimate of use_slot_engine / hash_dev: host-buffer calls currently inside the library
+    bgls_ctx* c;
+    explicit Busy(bgls_ctx* c_) : c(c_) { c->host_calls++; }
+    ~Busy() { c->host_calls--; }
+};
 static int pairing_host(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, size_t n, int do_final,
                         uint8_t* out, int* flag) {
     if (!ctx || !curve_ok(curve) || !out || (n && (!g1 || !g2))) return fail(ctx, BGLS_ERR_ARG, "bad argument");
-    struct Busy {   // load estimate of use_slot_engine
-        bgls_ctx* c;
-        explicit Busy(bgls_ctx* c_) : c(c_) { c->host_calls++; }
-        ~Busy() { c->host_calls--; }
-    } busy(ctx);
+    Busy busy(ctx);
     SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), b1 = align_up(n * 2 * F), b2 = align_up(n * 4 * F), bo = align_up(12 * F + 16);
@@ -1514,9 +1574,15 @@ int bgls_gt_pow(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* expon
 }
 static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_off, size_t n, void* d_out, cudaStream_t s) {
     if (n == 0) return BGLS_OK;
-    if (curve == BGLS_ALTBN128)
-        k_hash_to_g1_bn<BN254><<<(unsigned)((n * 8 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
-    else
+    if (curve == BGLS_ALTBN128) {
+        // several verifications in flight (or one large batch of messages): the pooled form does a third of the work;
+        // a lone verification keeps the one-round latency form.  BGLS_HASH=pool|wide overrides.
+        const bool pool = ctx->hash_mode == 1 || (ctx->hash_mode == 0 && n >= 64 && (busy_estimate(ctx) >= 3 || n >= 16384));
+        if (pool)
+            k_hash_to_g1_bn_pool<BN254><<<(unsigned)((n + 31) / 32), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+        else
+            k_hash_to_g1_bn<BN254><<<(unsigned)((n * 8 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    } else
         k_hash_to_g1_bls<BLS381><<<(unsigned)((n * 2 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -1584,6 +1650,7 @@ int bgls_verify_aggregate_signature(bgls_ctx* ctx, int curve, const uint8_t* msg
         for (size_t i = 0; i < n; i++)
             if (!seen.emplace(base + (total ? offsets[i] : 0), offsets[i + 1] - offsets[i]).second) return BGLS_OK;
     }
+    Busy busy(ctx);
     SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve), np = n + 1;
@@ -1619,6 +1686,7 @@ int bgls_verify_multi_signature(bgls_ctx* ctx, int curve, const uint8_t* msg, si
                                 const uint8_t* sig, int* ok) {
     if (!ctx || !curve_ok(curve) || !keys || !sig || !ok || n == 0 || (msg_len && !msg)) return fail(ctx, BGLS_ERR_ARG, "bad argument");
     *ok = 0;
+    Busy busy(ctx);
     SlotLock sl(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t F = fp_bytes(curve);

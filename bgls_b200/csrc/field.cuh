@@ -11,6 +11,7 @@
 #pragma once
 #include "arith.cuh"
 #include "curve_params.cuh"
+#include "inv.cuh"
 
 namespace bgls {
 
@@ -159,7 +160,19 @@ template <class C> HDNI void fp_pow(Fp<C>& r, const Fp<C>& a, const uint32_t* e,
     if (!started) fp_set(acc, C::R1());
     r = acc;
 }
-template <class C> HD void fp_inv(Fp<C>& r, const Fp<C>& a) { fp_pow(r, a, C::PM2(), C::N); }
+// r = a^-1 (Montgomery form in and out; a = 0 gives 0 as the Fermat power did).  Binary inversion of the limb value
+// a R (inv.cuh), the division by 2^k as two Montgomery products, then back to Montgomery form: (a R)^-1 R^2 = a^-1 R.
+template <class C> HD void fp_inv(Fp<C>& r, const Fp<C>& a) {
+    if (fp_is_zero(a)) { fp_zero(r); return; }
+    Fp<C> x, e1, e2, r2;
+    const int k = mp_almost_inv<C>(x.v, a.v);
+    inv_shift_limbs<C::N>(e1.v, e2.v, k);
+    fp_set(r2, C::R2());
+    fp_mul(x, x, e1);
+    fp_mul(x, x, e2);
+    fp_mul(x, x, r2);
+    fp_mul(r, x, r2);
+}
 
 // big-endian bytes (reference wire layout) <-> Montgomery limbs
 template <class C> HD void fp_from_be(Fp<C>& r, const uint8_t* be) {

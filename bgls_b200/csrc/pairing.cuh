@@ -320,12 +320,18 @@ template <class F> HDNI void jac_add(Jac<F>& r, const Jac<F>& p, const Jac<F>& q
     if (p.inf) { r = q; return; }
     if (q.inf) { r = p; return; }
     F Z1Z1, Z2Z2, U1, U2, S1, S2, H, R, t, HH, HHH, V;
+    F one;
+    fe_one(one);
+    const bool q_affine = fe_eq(q.Z, one);   // mixed addition (the addend of jac_mul, wire points): 4 products fewer
     fe_sqr(Z1Z1, p.Z);
-    fe_sqr(Z2Z2, q.Z);
-    fe_mul(U1, p.X, Z2Z2);
+    if (q_affine) { U1 = p.X; S1 = p.Y; }
+    else {
+        fe_sqr(Z2Z2, q.Z);
+        fe_mul(U1, p.X, Z2Z2);
+        fe_mul(t, q.Z, Z2Z2);
+        fe_mul(S1, p.Y, t);
+    }
     fe_mul(U2, q.X, Z1Z1);
-    fe_mul(t, q.Z, Z2Z2);
-    fe_mul(S1, p.Y, t);
     fe_mul(t, p.Z, Z1Z1);
     fe_mul(S2, q.Y, t);
     if (fe_eq(U1, U2)) {
@@ -348,8 +354,11 @@ template <class F> HDNI void jac_add(Jac<F>& r, const Jac<F>& p, const Jac<F>& q
     fe_mul(t, R, t);
     fe_mul(S1, S1, HHH);
     fe_sub(o.Y, t, S1);
-    fe_mul(t, p.Z, q.Z);
-    fe_mul(o.Z, t, H);
+    if (q_affine) fe_mul(o.Z, p.Z, H);
+    else {
+        fe_mul(t, p.Z, q.Z);
+        fe_mul(o.Z, t, H);
+    }
     r = o;
 }
 // scalar: 32 bytes big-endian

@@ -213,6 +213,42 @@ def test_hash_to_g1_reference_vectors_gpu(ctx, cid, c):
         assert got[i * rec:(i + 1) * rec] == w, i
 
 
+def test_pooled_try_and_increment_is_the_sequential_loop():
+    """altbn128 HashToG1 in its throughput form (k_hash_to_g1_bn_pool: a warp re-deals its lanes over the messages
+    still open every round) finds the counter the sequential loop of curves/hash.go:53-77 finds: reference vectors,
+    ragged message counts (partial warps) and 2,000 random messages against the oracle."""
+    import base64
+    import os
+    import bgls_b200
+    cid, c = CURVES[0]
+    old = os.environ.get("BGLS_HASH")
+    os.environ["BGLS_HASH"] = "pool"
+    try:
+        pctx = bgls_b200.Context(0)
+    finally:
+        if old is None:
+            del os.environ["BGLS_HASH"]
+        else:
+            os.environ["BGLS_HASH"] = old
+    try:
+        msgs, want = [], []
+        for line in open(os.path.join(os.path.dirname(__file__), "golden", "altbn128G1Hash.dat")):
+            m, pt = line.strip().split(",")
+            msgs.append(base64.b64decode(m))
+            want.append(base64.b64decode(pt))
+        rng = random.Random(41)
+        for k in range(2000):
+            m = bytes(rng.randrange(256) for _ in range(rng.choice((0, 1, 31, 32, 33, 135, 136, 200))))
+            msgs.append(m)
+            want.append(C.hash_to_g1(cid, m) if hasattr(C, "hash_to_g1") else c.marshal_g1(c.hash_to_g1(m)))
+        for n in (1, 5, 31, 32, 33, 64, len(msgs)):
+            got = pctx.hash_to_g1(cid, msgs[:n])
+            for i in range(n):
+                assert got[i * 64:(i + 1) * 64] == want[i], (n, i)
+    finally:
+        pctx.close()
+
+
 def test_scheme_layer_end_to_end():
     """bgls/bgls_test.go:19-77 (TestSingleSigner, TestAggregation) and bgls/blsKosk_test.go multisig shape, written
     against the engine-backed mirror of the reference API: every hash, scalar multiplication, point sum and pairing
