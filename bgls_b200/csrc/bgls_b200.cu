@@ -1101,12 +1101,16 @@ struct SlotLock {
     bool dev = false;
     // host-buffer call: any free slot, work runs on the slot's own stream
     explicit SlotLock(bgls_ctx* c) {
-        const unsigned start = c->rr.fetch_add(1);
-        for (int i = 0; i < NSLOT && !s; i++) {
-            Slot* t = &c->slots[(start + i) % NSLOT];
-            if (t->mu.try_lock()) s = t;
-        }
-        if (!s) { s = &c->slots[start % NSLOT]; s->mu.lock(); }
+        // the highest free slot that no device-resident stream owns (those are handed out from index 0 up): a caller that
+        // makes one call after another keeps getting the same slot, whose scratch has already grown to its sizes; C
+        // concurrent callers settle on C slots.  (Round robin made each of the first NSLOT calls pay a scratch allocation.)
+        for (int pass = 0; pass < 2 && !s; pass++)
+            for (int i = NSLOT - 1; i >= 0 && !s; i--) {
+                Slot* t = &c->slots[i];
+                if (pass == 0 && t->owned) continue;   // unlocked read: a hint only
+                if (t->mu.try_lock()) s = t;
+            }
+        if (!s) { s = &c->slots[NSLOT - 1 - c->rr.fetch_add(1) % NSLOT]; s->mu.lock(); }
         bool had = false;
         {
             std::lock_guard<std::mutex> lk(c->own_mu);
