@@ -927,6 +927,9 @@ template <class C, class T, class F> int upload_slot(bgls_ctx* ctx, SlotEngDev& 
     // carve-outs cannot share an SM, and an SM drains before it switches (measured: the pipeline was capped at 2.6 M
     // pairings/s however many products were in flight, the Miller kernel alone reached 3.5 M)
     CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB, FIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_slot_finish_bytes<C, T, SLOT_WPB, FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)std::max(sv_smem_bytes<C, T, NPB>(), FIN::SMEM_BYTES)));
+    CU(cudaFuncSetAttribute(k_slot_finish_bytes<C, T, SLOT_WPB, FIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return BGLS_OK;
 }
 size_t slot_blocks(size_t n) { return (n + SLOT_PAIRS_PER_BLOCK - 1) / SLOT_PAIRS_PER_BLOCK; }
@@ -971,6 +974,19 @@ int slot_pairing(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const u
     k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, n, levels, tl_slot->tickets, mval, T::MACH_L, fa, SvBatch{}, ctx->trace);
     ctx->launches++;
     if (ctx->profiling) { cudaEventRecord(ctx->ev[1], s); cudaEventRecord(ctx->ev[2], s); }
+    CU(cudaGetLastError());
+    return BGLS_OK;
+}
+// product of k wire-form Miller values (k <= SLOT_FANIN) + final exponentiation / export in one launch
+template <class C, class T, class F>
+int slot_finish_bytes(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const uint8_t* d_partials, size_t k, int do_final, uint8_t* d_out,
+                      int* d_flag, void* work, cudaStream_t s) {
+    using FIN = MachFinisher<F>;
+    constexpr int NPB = SLOT_WPB * 32 / T::G;
+    constexpr size_t smem = std::max(sv_smem_bytes<C, T, NPB>(), FIN::SMEM_BYTES);
+    MachFinishArgs fa{md.f, do_final ? md.finalexp : md.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN, d_out, d_flag, nullptr};
+    k_slot_finish_bytes<C, T, SLOT_WPB, FIN><<<1, SLOT_WPB * 32, smem, s>>>(se.tb, d_partials, (int)k, (uint32_t*)work, T::MACH_L, fa);
+    ctx->launches++;
     CU(cudaGetLastError());
     return BGLS_OK;
 }
@@ -1060,6 +1076,14 @@ int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, si
 }
 int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s) {
     if (ctx->thread_engine) return finish_bytes_dev_thread(ctx, curve, d_partials, k, do_final, d_out, d_flag, s);
+    // throughput regime (several verifications in flight): one launch on the slot engine instead of import + tree + finish
+    if (k <= SLOT_FANIN && (ctx->engine == ENGINE_SLOT || (ctx->engine == ENGINE_AUTO && busy_estimate(ctx) >= SLOT_MIN_BUSY))) {
+        if (curve == BGLS_ALTBN128)
+            return slot_finish_bytes<BN254, SlotBN, mtab::BN254_F>(ctx, ctx->sloteng[0], ctx->mach[0], (const uint8_t*)d_partials, k, do_final,
+                                                                   (uint8_t*)d_out, (int*)d_flag, work, s);
+        return slot_finish_bytes<BLS381, SlotBLS, mtab::BLS381_F>(ctx, ctx->sloteng[1], ctx->mach[1], (const uint8_t*)d_partials, k, do_final,
+                                                                  (uint8_t*)d_out, (int*)d_flag, work, s);
+    }
     if (curve == BGLS_ALTBN128)
         return mach_finish_bytes<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
     return mach_finish_bytes<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);

@@ -483,6 +483,42 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
     }
 }
 
+// Finishing step of a sharded verification in ONE launch: the product of k <= 2 NPB Miller values in wire form (the
+// all-gathered partials of the ranks, /root/reference/curves/curve.go:141-169 across GPUs) and FIN on it -- the final
+// exponentiation and the comparison with the identity, or the plain export.  Replaces import + tree + finish (three
+// dependent launches per step, which cost the multi-GPU pipeline a tenth of its throughput).
+template <class C, class T, int WPB, class FIN>
+__global__ void __launch_bounds__(WPB * 32) k_slot_finish_bytes(SvTables tb, const uint8_t* __restrict__ vals, int k, uint32_t* __restrict__ mach_out,
+                                                                int mach_l, typename FIN::Args fin) {
+    constexpr int N = C::N, FB = C::FP_BYTES, G = T::G, NPB = WPB * 32 / G, W4 = 2 * N / 4, GPW = 32 / G;
+    extern __shared__ uint4 sv_sm[];
+    SvU4* consts = (SvU4*)sv_sm;
+    SvU4* slots = consts + T::NCONST * W4;
+    for (int i = threadIdx.x; i < T::NCONST * 2 * N; i += blockDim.x) ((uint32_t*)consts)[i] = tb.consts[i];
+    const int lane = threadIdx.x & 31;
+    const int q = (threadIdx.x >> 5) * GPW + lane % GPW, gl = lane / GPW;
+    const SlotFile<C, NPB> sf{slots, consts, q, 0};
+    __syncthreads();
+    // group q: F <- value 2q, G <- value 2q + 1.  Wire position t (coefficient t / 2 of sv_wire_slot, im before re).
+    for (int t = gl; t < 24; t += G) {
+        const int which = t / 12, w = t % 12, v = 2 * q + which;
+        if (v < k) {
+            const LN<N> x = sv_fp_from_be<C>(vals + ((size_t)v * 12 + w) * FB);
+            sf.store_fp(sv_wire_slot<T>(w >> 1) + (which ? T::S_G00 - T::S_F00 : 0), (w & 1) ? 0 : 1, x);
+        }
+    }
+    if (k == 0 && q == 0 && gl == 0) sv_set_one<C, T, NPB>(sf);   // the empty product
+    __syncthreads();
+    sv_run<C, NPB, G>(slots, consts, q, 0, tb.code, tb.offs[T::P_MUL12], tb.offs[T::P_MUL12 + 1], gl, 2 * q + 1 < k);
+    sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, (k + 1) / 2);
+    sv_emit_value<C, T, NPB>(slots, consts, tb, mach_out, mach_l);
+    if (FIN::SMEM_BYTES) {
+        __threadfence_block();
+        __syncthreads();
+        if (threadIdx.x < 32) FIN::run((uint32_t*)sv_sm, fin, mach_out);
+    }
+}
+
 #endif
 
 }  // namespace bgls

@@ -120,3 +120,25 @@ def test_slot_batch_ragged(sctx, cid, c):
         offs.append(offs[-1] + n)
     assert sctx.pairing_check_batch(cid, b"".join(g1s), b"".join(g2s), offs) == exp
     assert any(exp) and not all(exp)
+
+
+@pytest.mark.parametrize("cid,c", CURVES)
+def test_slot_finish_of_gathered_partials(sctx, cid, c):
+    """The finishing step of a sharded verification on the slot engine (k_slot_finish_bytes: product of the k gathered
+    wire-form partials + final exponentiation in one launch) against the oracle's product of the same bytes, for every
+    k one block covers (1..8) and beyond (9: the machine's import / tree / finish path)."""
+    rng = random.Random(900 + cid)
+    nb = c.nbytes
+    parts = b""
+    for k in range(1, 10):
+        g1, _ = rand_points(cid, c, 1, 3, rng)
+        g2, _ = rand_points(cid, c, 2, 3, rng)
+        parts += sctx.miller_product(cid, g1, g2, 3)
+        assert len(parts) == 12 * nb * k
+        gt, one = sctx.final_exp_product(cid, parts, k)
+        assert not one and gt == C.fp12_product(cid, parts, k, True), k
+    g1, g2 = make_aggregate(cid, c, 23, rng)
+    cut = [0, 5, 6, 13, 24]
+    shards = b"".join(sctx.miller_product(cid, g1[2 * nb * a:2 * nb * b], g2[4 * nb * a:4 * nb * b], b - a) for a, b in zip(cut, cut[1:]))
+    gt, one = sctx.final_exp_product(cid, shards, 4)
+    assert one and gt == c.marshal_gt(c.fp12_one)
