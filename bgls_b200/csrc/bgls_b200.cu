@@ -298,19 +298,22 @@ __global__ void __launch_bounds__(TB) k_hash_to_g1_bn(const uint8_t* __restrict_
         if (__all_sync(0xFFFFFFFFu, done)) break;
     }
 }
-// altbn128, throughput form: a warp owns 32 messages and deals its lanes out again every round -- lane L tries counter
+// altbn128, throughput form: a warp owns 32 messages and deals its lanes out again every round -- lane L tests counter
 // next[m] + L / u of the (L mod u)-th unfinished message m, u = messages still open.  Round 1 is one counter per message
-// (half succeed), round 2 two counters for each of the ~16 left, round 3 eight for the ~4 left: ~3 square-root
-// exponentiations per message instead of the 8 of the latency form above.  The lowest successful counter of a message
-// wins, exactly what the sequential loop of hash.go:53-77 finds first.
+// (half succeed), round 2 two counters for each of the ~16 left, round 3 eight for the ~4 left.  The test of a counter is
+// a Jacobi symbol (inv.cuh), not the square root: the one exponentiation per message runs after the search, on the
+// lane that owns the message -- ~3 cheap tests + 1 exponentiation per message instead of the 8 exponentiations of the
+// latency form above.  The lowest successful counter of a message wins, exactly what the sequential loop of
+// hash.go:53-77 finds first.
 template <class C>
 __global__ void __launch_bounds__(TB) k_hash_to_g1_bn_pool(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
                                                            uint8_t* __restrict__ out) {
     static_assert(TB == 32, "one warp per block");
     const int lane = threadIdx.x;
     const size_t base = (size_t)blockIdx.x * 32;
-    bool done = base + lane >= n;
-    unsigned next = 0;                                   // next counter of this lane's own message
+    const bool mine = base + lane < n;
+    bool done = !mine;
+    unsigned next = 0, won = 0;                          // next counter to test / the counter found, of this lane's own message
     for (;;) {
         const unsigned pending = __ballot_sync(0xFFFFFFFFu, !done);
         if (!pending) break;
@@ -319,21 +322,23 @@ __global__ void __launch_bounds__(TB) k_hash_to_g1_bn_pool(const uint8_t* __rest
         const int owner = __fns(pending, 0, slot + 1);   // lane that owns the slot-th open message
         const unsigned counter = __shfl_sync(0xFFFFFFFFu, next, owner) + rep;
         const size_t i = base + owner;
+        const bool ok = rep < per && counter < 256 && bn_hash_test<C>((uint8_t)counter, msgs + off[i], (size_t)(off[i + 1] - off[i]));
+        const unsigned hits = __ballot_sync(0xFFFFFFFFu, ok);
+        if (!done) {
+            const int myslot = __popc(pending & ((1u << lane) - 1u));
+            for (int r = 0; r < per && !done; r++)
+                if ((hits >> (myslot + r * u)) & 1u) { won = next + r; done = true; }
+            if (!done && next + per >= 256) { won = 256; done = true; }   // 256 failures: probability 2^-256, the reference would spin
+            next += per;
+        }
+    }
+    if (mine && won < 256) {
+        const size_t i = base + lane;
         const uint8_t* m = msgs + off[i];
         const size_t len = (size_t)(off[i + 1] - off[i]);
         Fp<C> px, root;
-        const bool ok = rep < per && counter < 256 && bn_hash_try<C>(px, root, (uint8_t)counter, m, len);
-        const unsigned hits = __ballot_sync(0xFFFFFFFFu, ok);
-        bool lower = false;                              // a smaller counter of the same message succeeded
-        for (int r = 0; r < rep; r++) lower |= (hits >> (slot + r * u)) & 1u;
-        if (ok && !lower) bn_hash_finish<C>(out + i * 2 * C::FP_BYTES, px, root, m, len);
-        if (!done) {
-            const int myslot = __popc(pending & ((1u << lane) - 1u));
-            bool any = false;
-            for (int r = 0; r < per; r++) any |= (hits >> (myslot + r * u)) & 1u;
-            if (any || next + per >= 256) done = true;   // 256 failures: probability 2^-256, the reference would spin
-            next += per;
-        }
+        bn_hash_try<C>(px, root, (uint8_t)won, m, len);
+        bn_hash_finish<C>(out + i * 2 * C::FP_BYTES, px, root, m, len);
     }
 }
 template <class C>

@@ -132,13 +132,9 @@ HD void blake2b512_tagged(uint8_t* digest, const uint8_t* msg, size_t len, const
 
 // ---------------------------------------------------------------- field helpers for the encodings
 template <class C> HD void fp_sqrt_candidate(Fp<C>& r, const Fp<C>& a) { fp_pow(r, a, C::PP1D4(), C::N); }  // hash.go:178-190
-template <class C> HD bool fp_is_quad_res(const Fp<C>& a) {                                                  // hash.go:254-265
-    if (fp_is_zero(a)) return true;
-    Fp<C> e, one;
-    fp_pow(e, a, C::PM1D2(), C::N);
-    fp_set(one, C::R1());
-    return fp_eq(e, one);
-}
+// isQuadRes (hash.go:254-265: Euler's criterion, 0 counts as a residue) by the binary Jacobi symbol (inv.cuh): the symbol
+// of the Montgomery residue a R is that of a because R is a square
+template <class C> HD bool fp_is_quad_res(const Fp<C>& a) { return mp_jacobi<C>(a.v) >= 0; }
 // parity(x): x > q - x  <=>  canonical x > (q-1)/2                                                           hash.go:169-172
 template <class C> HD bool fp_parity(const Fp<C>& a) {
     Fp<C> one, x;
@@ -190,6 +186,15 @@ template <class C> HD bool bn_hash_try(Fp<C>& px, Fp<C>& root, uint8_t counter, 
     fp_sqrt_candidate(root, y2);
     fp_sqr(chk, root);
     return fp_eq(chk, y2);
+}
+// the same test without the square root (Jacobi symbol): which counter the loop stops at
+template <class C> HD bool bn_hash_test(uint8_t counter, const uint8_t* msg, size_t len) {
+    uint8_t h[32];
+    keccak256_prefixed(h, counter, msg, len);
+    Fp<C> px, y2;
+    fp_from_digest32<C>(px, h);
+    g1_x_to_y2(y2, px);
+    return fp_is_quad_res(y2);
 }
 // the sign of y comes from keccak(255 || msg) (hash.go:68-72)
 template <class C> HD void bn_hash_finish(uint8_t* out, const Fp<C>& px, Fp<C>& root, const uint8_t* msg, size_t len) {
@@ -247,28 +252,23 @@ template <class C> HD void sw_encode(Fp<C>& x, Fp<C>& y, const Fp<C>& t) {
     fp_sub(x0, z, tmp);     // x0 = z - t w
     fp_neg(x1, x0);
     fp_sub(x1, x1, one);    // x1 = -1 - x0
-    // the candidates are tested in the reference's order (hash.go:120-160); the residue test and the square root
-    // share one exponentiation: r = v^((q+1)/4) is a root iff r^2 == v (0 counts as a residue, hash.go:254-265)
-    Fp<C> chk;
+    // the candidates are tested in the reference's order (hash.go:120-160): x0, then x1, else x2.  The residue tests are
+    // Jacobi symbols, so every lane runs exactly ONE square-root exponentiation (three in lockstep before)
     x = x0;
     g1_x_to_y2(y2, x0);
-    fp_sqrt_candidate(y, y2);
-    fp_sqr(chk, y);
-    if (!fp_eq(chk, y2)) {
+    if (!fp_is_quad_res(y2)) {
         x = x1;
         g1_x_to_y2(y2, x1);
-        fp_sqrt_candidate(y, y2);
-        fp_sqr(chk, y);
-        if (!fp_eq(chk, y2)) {
+        if (!fp_is_quad_res(y2)) {
             fp_mul(tmp, A, inv);    // 1/B
             fp_mul(tmp, A, tmp);    // A/B = 1/w
             fp_sqr(tmp, tmp);
             fp_add(x2, tmp, one);   // x2 = 1 + 1/w^2
             x = x2;
             g1_x_to_y2(y2, x2);
-            fp_sqrt_candidate(y, y2);
         }
     }
+    fp_sqrt_candidate(y, y2);
     if (fp_parity(y) != fp_parity(t)) fp_neg(y, y);
 }
 template <class C> HD void ft_point(Jac<Fp<C>>& P, const uint8_t* digest64) {

@@ -120,6 +120,56 @@ template <class C> INV_NOINLINE int mp_almost_inv(uint32_t* x, const uint32_t* a
     mpw_sub<N>(x, pp, r);
     return k;
 }
+// Jacobi symbol (a / p) of 0 <= a < p (N plain limbs; for a Montgomery residue a R the symbol is that of a, R being a
+// square): -1, 0 (a = 0) or 1.  Binary algorithm -- subtract the smaller of two odd numbers from the larger, strip the
+// zero bits with the (2 / n) rule, quadratic reciprocity whenever numerator and denominator change roles -- about 380
+// iterations of one subtraction and one shift for a 381-bit prime: the residuosity test of hash-to-G1
+// (/root/reference/curves/hash.go:254-265, a ~476-multiplication exponentiation there) for the price of ~27.
+template <class C> INV_NOINLINE int mp_jacobi(const uint32_t* a) {
+    constexpr int N = C::N;
+    uint32_t A[N], B[N], d[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { A[i] = a[i]; B[i] = C::p(i); }
+    if (mpw_is_zero<N>(A)) return 0;
+    int t = 1;
+    bool num_is_a = true;                         // which array is the numerator of the current symbol
+    while (!(A[0] & 1u)) {                        // (2 / p)^tz
+        const int tz = inv_ctz31(A[0]);
+        mpw_shr<N>(A, tz);
+        if ((tz & 1) && (((B[0] & 7u) == 3u) || ((B[0] & 7u) == 5u))) t = -t;
+    }
+#pragma unroll 1
+    for (;;) {
+        const uint32_t br = mpw_sub<N>(d, A, B);  // A - B
+        if (!br) {
+            if (d[0] == 0 && mpw_is_zero<N>(d)) break;                     // A = B = gcd
+            if (!num_is_a) {                                               // (B / A) -> (A / B): reciprocity
+                if ((A[0] & 3u) == 3u && (B[0] & 3u) == 3u) t = -t;
+                num_is_a = true;
+            }
+            do {
+                const int tz = inv_ctz31(d[0]);
+                mpw_shr<N>(d, tz);
+                if ((tz & 1) && (((B[0] & 7u) == 3u) || ((B[0] & 7u) == 5u))) t = -t;
+            } while (!(d[0] & 1u));
+#pragma unroll
+            for (int i = 0; i < N; i++) A[i] = d[i];
+        } else {
+            if (num_is_a) {
+                if ((A[0] & 3u) == 3u && (B[0] & 3u) == 3u) t = -t;
+                num_is_a = false;
+            }
+            mpw_sub<N>(B, B, A);
+            do {
+                const int tz = inv_ctz31(B[0]);
+                mpw_shr<N>(B, tz);
+                if ((tz & 1) && (((A[0] & 7u) == 3u) || ((A[0] & 7u) == 5u))) t = -t;
+            } while (!(B[0] & 1u));
+        }
+    }
+    return (A[0] == 1u && mpw_is_zero<N - 1>(A + 1)) ? t : 0;
+}
+
 // the two exponents of x 2^-k = mont(mont(x, 2^j1), 2^j2), mont(a, b) = a b 2^(-32 N):  j1 + j2 = 64 N - k
 template <int N> HD void inv_shift_limbs(uint32_t* e1, uint32_t* e2, int k) {
     const int j = 64 * N - k, j1 = j < 32 * N - 1 ? j : 32 * N - 1, j2 = j - j1;

@@ -62,3 +62,5 @@ extern "C" int emu_inv_plain(int curve, const uint32_t* a, uint32_t* out) {
     else { LN<12> x; memcpy(x.v, a, 48); x = mp_inv_plain<BLS381>(x); memcpy(out, x.v, 48); }
     return 0;
 }
+// Jacobi symbol (a / p) of the N-limb value a
+extern "C" int emu_jacobi(int curve, const uint32_t* a) { return curve == 0 ? mp_jacobi<BN254>(a) : mp_jacobi<BLS381>(a); }

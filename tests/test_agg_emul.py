@@ -62,3 +62,14 @@ def test_binary_inversion(emu, curve, N):
         out = (ctypes.c_uint32 * N)()
         emu.emu_inv_plain(curve, inp, out)
         assert sum(w << (32 * i) for i, w in enumerate(out)) == pow(a, -1, p)
+
+
+@pytest.mark.parametrize("curve,N", [(0, 8), (1, 12)])
+def test_jacobi_symbol(emu, curve, N):
+    """inv.cuh mp_jacobi against Euler's criterion: the residuosity test of hash-to-G1."""
+    p = CURVES[curve][1].p
+    rng = random.Random(6)
+    for a in [0, 1, 2, 3, 4, p - 1, p - 2, (p - 1) // 2, 1 << 200, (1 << 200) + 1] + [rng.randrange(1, p) for _ in range(400)]:
+        inp = (ctypes.c_uint32 * N)(*[(a >> (32 * i)) & 0xFFFFFFFF for i in range(N)])
+        e = pow(a, (p - 1) // 2, p)
+        assert emu.emu_jacobi(curve, inp) == (0 if a == 0 else 1 if e == 1 else -1), a
