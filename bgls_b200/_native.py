@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libbgls_b200.so")
+LIB_PATH = os.environ.get("BGLS_LIB_PATH") or os.path.join(HERE, "lib", "libbgls_b200.so")   # BGLS_LIB_PATH: A/B builds of the same ABI
 
 ALTBN128, BLS12_381 = 0, 1
 G1, G2 = 1, 2

@@ -906,7 +906,10 @@ int mach_batch(bgls_ctx* ctx, const MachDev& d, const uint8_t* d_g1, const uint8
 // (profiles/r2_l_*: altbn128 4.1 M pairings/s with the GPU full against 3.7 for 4 lanes per pair, 3.6 for 8 lanes per pair)
 using SlotBN = svt::BN254_G8K2;
 using SlotBLS = svt::BLS381_G8K2;
-constexpr int SLOT_WPB = 1;   // one warp per block: 4 groups = 8 pairs, 14 / 21 KB of shared memory -> 15 / 8 resident warps per SM
+#ifndef BGLS_SLOT_WPB
+#define BGLS_SLOT_WPB 1
+#endif
+constexpr int SLOT_WPB = BGLS_SLOT_WPB;   // one warp per block: 4 groups = 8 pairs, 14 / 21 KB of shared memory -> 15 / 8 resident warps per SM
 constexpr size_t SLOT_PAIRS_PER_BLOCK = (size_t)SLOT_WPB * 32 / SlotBN::G * SlotBN::K;
 static_assert(SlotBN::G == SlotBLS::G && SlotBN::K == SlotBLS::K, "one block shape for both curves");
 template <class C, class T, class F> int upload_slot(bgls_ctx* ctx, SlotEngDev& d) {
