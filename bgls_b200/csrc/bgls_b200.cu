@@ -589,7 +589,8 @@ size_t jac_dev_bytes(int c, int g) {
 
 // ---- enqueue helpers (device pointers); `work` is device scratch owned by the caller
 size_t agg_work_bytes(int curve, int group, size_t n) {
-    const size_t nb = (n + 19) / 20 + 1, words = 3 * (size_t)group * (curve == BGLS_ALTBN128 ? 8 : 12);
+    // the grid never exceeds SMs x resident blocks per SM (agg_grid): 4096 bounds it on any part
+    const size_t nb = std::min<size_t>((n + 19) / 20 + 1, 4096), words = 3 * (size_t)group * (curve == BGLS_ALTBN128 ? 8 : 12);
     return align_up((agg_tree_values(nb, 20) + 1) * words * 4);
 }
 template <class C>
@@ -633,7 +634,7 @@ template <class E> int agg_blocks_per_sm(bgls_ctx* ctx, int* out) {
 }
 size_t agg_grid(size_t n, int sms, int per_sm) {
     size_t nb = (n + AGG_NGB - 1) / AGG_NGB;
-    const size_t cap = (size_t)sms * per_sm;
+    const size_t cap = std::min<size_t>((size_t)sms * per_sm, 4095);
     if (nb > cap) nb = cap;
     return nb ? nb : 1;
 }
