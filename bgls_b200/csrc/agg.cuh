@@ -304,6 +304,11 @@ inline size_t agg_tree_values(size_t nb, size_t fan) {
     for (size_t c = nb; c > 1; c = (c + fan - 1) / fan) w += c;
     return w;
 }
+inline size_t agg_tree_tickets(size_t nb, size_t fan) {
+    size_t k = 0;
+    for (size_t c = nb; c > 1; c = (c + fan - 1) / fan) k += (c + fan - 1) / fan;
+    return k;
+}
 
 #if defined(__CUDACC__)
 

@@ -646,7 +646,7 @@ int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, uint8_t* d_
     if (rc) return rc;
     if (ctx->agg_blocks_per_sm > 0 && ctx->agg_blocks_per_sm < per_sm) per_sm = ctx->agg_blocks_per_sm;
     const size_t nb = agg_grid(n, ctx->sms, per_sm);
-    rc = ensure_tickets(ctx, tl_slot, nb / AGG_NGB + 8);
+    rc = ensure_tickets(ctx, tl_slot, agg_tree_tickets(nb, AGG_NGB) + 1);
     if (rc) return rc;
     k_agg<E, AGG_WPB><<<(unsigned)nb, AGG_WPB * 32, agg_smem_bytes<E, AGG_NGB>(), s>>>(d_pts, n, (uint32_t*)work, tl_slot->tickets, d_out, nullptr);
     ctx->launches++;
