@@ -654,9 +654,17 @@ int enqueue_aggregate(bgls_ctx* ctx, const uint8_t* d_pts, size_t n, uint8_t* d_
     return BGLS_OK;
 }
 
+// peers / fused_send: the multi-GPU exchange rides in the slot engine's launch when that engine runs (then *fused_send = true)
 int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
-                void* d_flag, void* work, cudaStream_t s);
-int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s);
+                void* d_flag, void* work, cudaStream_t s, const SvPeers* peers = nullptr, bool* fused_send = nullptr);
+// the same for the waiting side: the bounded wait for the peers' flags opens the slot engine's finishing launch (*fused_wait = true)
+struct XchWait {
+    const unsigned long long* flags;
+    unsigned long long epoch;
+    int* err;
+};
+int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s,
+                     const XchWait* wait = nullptr, bool* fused_wait = nullptr);
 int batch_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, const void* d_off, size_t nbatch, size_t total,
               void* d_ok, void* work, cudaStream_t s);
 
@@ -966,7 +974,7 @@ int ensure_tickets(bgls_ctx* ctx, Slot* sl, size_t count) {
 // k_slot_miller with the low-footprint finisher as the tail of the block that ends up with the product.
 template <class C, class T, class F>
 int slot_pairing(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const uint8_t* d_g1, const uint8_t* d_g2, size_t n, int do_final,
-                 uint8_t* d_out, int* d_flag, void* work, cudaStream_t s) {
+                 uint8_t* d_out, int* d_flag, void* work, cudaStream_t s, const SvPeers* peers = nullptr) {
     using FIN = MachFinisher<F>;
     constexpr int NPB = SLOT_WPB * 32 / T::G;
     constexpr size_t smem = std::max(sv_smem_bytes<C, T, NPB>(), FIN::SMEM_BYTES);
@@ -980,7 +988,8 @@ int slot_pairing(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const u
     uint32_t* mval = (uint32_t*)((char*)levels + align_up((sv_tree_words(nb, SLOT_FANIN, C::N) + 1) * 4));
     MachFinishArgs fa{md.f, do_final ? md.finalexp : md.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN, d_out, d_flag, nullptr};
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
-    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, n, levels, tl_slot->tickets, mval, T::MACH_L, fa, SvBatch{}, ctx->trace);
+    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, n, levels, tl_slot->tickets, mval, T::MACH_L, fa, SvBatch{}, ctx->trace,
+                                                                                 peers ? *peers : SvPeers{});
     ctx->launches++;
     if (ctx->profiling) { cudaEventRecord(ctx->ev[1], s); cudaEventRecord(ctx->ev[2], s); }
     CU(cudaGetLastError());
@@ -989,12 +998,13 @@ int slot_pairing(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const u
 // product of k wire-form Miller values (k <= SLOT_FANIN) + final exponentiation / export in one launch
 template <class C, class T, class F>
 int slot_finish_bytes(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const uint8_t* d_partials, size_t k, int do_final, uint8_t* d_out,
-                      int* d_flag, void* work, cudaStream_t s) {
+                      int* d_flag, void* work, cudaStream_t s, const XchWait* wait = nullptr) {
     using FIN = MachFinisher<F>;
     constexpr int NPB = SLOT_WPB * 32 / T::G;
     constexpr size_t smem = std::max(sv_smem_bytes<C, T, NPB>(), FIN::SMEM_BYTES);
     MachFinishArgs fa{md.f, do_final ? md.finalexp : md.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN, d_out, d_flag, nullptr};
-    k_slot_finish_bytes<C, T, SLOT_WPB, FIN><<<1, SLOT_WPB * 32, smem, s>>>(se.tb, d_partials, (int)k, (uint32_t*)work, T::MACH_L, fa);
+    k_slot_finish_bytes<C, T, SLOT_WPB, FIN><<<1, SLOT_WPB * 32, smem, s>>>(se.tb, d_partials, (int)k, (uint32_t*)work, T::MACH_L, fa,
+                                                                            wait ? wait->flags : nullptr, wait ? wait->epoch : 0ull, wait ? wait->err : nullptr);
     ctx->launches++;
     CU(cudaGetLastError());
     return BGLS_OK;
@@ -1024,7 +1034,7 @@ int slot_batch(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const uin
     k_slot_plan<<<1, 1024, 0, s>>>(d_off, nbatch, (unsigned)SLOT_PAIRS_PER_BLOCK, (unsigned)SLOT_FANIN, bstart, lstart, tstart);
     MachFinishArgs fa{md.f, md.finalexp, F::FINALEXP_LEN, nullptr, nullptr, nullptr};
     SvBatch b{d_off, bstart, lstart, tstart, nbatch, d_ok};
-    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, 0, levels, tl_slot->tickets, mvals, T::MACH_L, fa, b, ctx->trace);
+    k_slot_miller<C, T, SLOT_WPB, FIN><<<(unsigned)nb, SLOT_WPB * 32, smem, s>>>(se.tb, d_g1, d_g2, 0, levels, tl_slot->tickets, mvals, T::MACH_L, fa, b, ctx->trace, SvPeers{});
     ctx->launches += 2;
     CU(cudaGetLastError());
     return BGLS_OK;
@@ -1052,16 +1062,19 @@ size_t mach_work_for(int curve, size_t n) {
     return curve == BGLS_ALTBN128 ? mach_work_bytes<mtab::BN254_M>(n) : mach_work_bytes<mtab::BLS381_M>(n);
 }
 int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, size_t n, int do_final, void* d_out,
-                void* d_flag, void* work, cudaStream_t s) {
+                void* d_flag, void* work, cudaStream_t s, const SvPeers* peers, bool* fused_send) {
+    if (fused_send) *fused_send = false;
     if (ctx->thread_engine) return pairing_dev_thread(ctx, curve, d_g1, d_g2, n, do_final, d_out, d_flag, work, s, ctx->profiling);
     if (use_slot_engine(ctx, n)) {
         // throughput regime: Miller loops and product tree on the slot engine (saturated limbs, 8 lanes per group of 2 pairs
         // that share their accumulator), then the machine's final exponentiation in its low-footprint form
+        if (fused_send && peers && !do_final) *fused_send = true;
+        const SvPeers* pp = (fused_send && *fused_send) ? peers : nullptr;
         if (curve == BGLS_ALTBN128)
             return slot_pairing<BN254, SlotBN, mtab::BN254_F>(ctx, ctx->sloteng[0], ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2,
-                                                                              n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+                                                                              n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s, pp);
         return slot_pairing<BLS381, SlotBLS, mtab::BLS381_F>(ctx, ctx->sloteng[1], ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2,
-                                                                              n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
+                                                                              n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s, pp);
     }
     if (n >= MHYBRID && !ctx->machine_only) {
         // throughput regime: the thread-per-pair Miller kernel (Karatsuba towers, saturated limbs) does ~1.45x more
@@ -1083,15 +1096,20 @@ int pairing_dev(bgls_ctx* ctx, int curve, const void* d_g1, const void* d_g2, si
         return mach_pairing<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
     return mach_pairing<mtab::BLS381_M, mtab::BLS381_F>(ctx, ctx->mach[1], (const uint8_t*)d_g1, (const uint8_t*)d_g2, n, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
 }
-int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s) {
+int finish_bytes_dev(bgls_ctx* ctx, int curve, const void* d_partials, size_t k, int do_final, void* d_out, void* d_flag, void* work, cudaStream_t s,
+                     const XchWait* wait, bool* fused_wait) {
+    if (fused_wait) *fused_wait = false;
     if (ctx->thread_engine) return finish_bytes_dev_thread(ctx, curve, d_partials, k, do_final, d_out, d_flag, s);
     // throughput regime (several verifications in flight): one launch on the slot engine instead of import + tree + finish
-    if (k <= SLOT_FANIN && (ctx->engine == ENGINE_SLOT || (ctx->engine == ENGINE_AUTO && busy_estimate(ctx) >= SLOT_MIN_BUSY))) {
+    // (a caller that passes `wait` has already decided for this path and launched no wait kernel)
+    if (k <= SLOT_FANIN && (wait || ctx->engine == ENGINE_SLOT || (ctx->engine == ENGINE_AUTO && busy_estimate(ctx) >= SLOT_MIN_BUSY))) {
+        const XchWait* w = (wait && fused_wait && d_flag) ? wait : nullptr;
+        if (w) *fused_wait = true;
         if (curve == BGLS_ALTBN128)
             return slot_finish_bytes<BN254, SlotBN, mtab::BN254_F>(ctx, ctx->sloteng[0], ctx->mach[0], (const uint8_t*)d_partials, k, do_final,
-                                                                   (uint8_t*)d_out, (int*)d_flag, work, s);
+                                                                   (uint8_t*)d_out, (int*)d_flag, work, s, w);
         return slot_finish_bytes<BLS381, SlotBLS, mtab::BLS381_F>(ctx, ctx->sloteng[1], ctx->mach[1], (const uint8_t*)d_partials, k, do_final,
-                                                                  (uint8_t*)d_out, (int*)d_flag, work, s);
+                                                                  (uint8_t*)d_out, (int*)d_flag, work, s, w);
     }
     if (curve == BGLS_ALTBN128)
         return mach_finish_bytes<mtab::BN254_M, mtab::BN254_F>(ctx, ctx->mach[0], (const uint8_t*)d_partials, k, do_final, (uint8_t*)d_out, (int*)d_flag, work, s);
@@ -1889,17 +1907,24 @@ int bgls_miller_product_exchange_dev(bgls_ctx* ctx, int curve, const void* d_g1,
     int rc = dev_work(ctx, sl.s, bw + align_up(rec + 16), &work);
     if (rc) return rc;
     uint8_t* partial = (uint8_t*)work + bw;
-    rc = pairing_dev(ctx, curve, d_g1, d_g2, n, 0, partial, nullptr, work, (cudaStream_t)stream);
-    if (rc) return rc;
     PeerPtrs pp{};
+    SvPeers sp{};
     const int parity = (int)(epoch & 1);
     for (int r = 0; r < x.world; r++) {
-        pp.slot[r] = x.peer[r] + xch_rec_off(x, lane, parity, x.rank, rec);
-        pp.flag[r] = (unsigned long long*)(x.peer[r] + xch_flag_off(x, lane, parity, x.rank));
+        sp.slot[r] = pp.slot[r] = x.peer[r] + xch_rec_off(x, lane, parity, x.rank, rec);
+        sp.flag[r] = pp.flag[r] = (unsigned long long*)(x.peer[r] + xch_flag_off(x, lane, parity, x.rank));
     }
-    // broadcast over peer memory: one tiny kernel, payload then flag
-    k_exchange_send_t<PeerPtrs><<<1, 256, 0, (cudaStream_t)stream>>>(partial, (int)rec, pp, x.world, (unsigned long long)epoch);
-    ctx->launches++;
+    sp.world = x.world;
+    sp.nbytes = (int)rec;
+    sp.epoch = (unsigned long long)epoch;
+    bool fused = false;
+    rc = pairing_dev(ctx, curve, d_g1, d_g2, n, 0, partial, nullptr, work, (cudaStream_t)stream, &sp, &fused);
+    if (rc) return rc;
+    if (!fused) {
+        // broadcast over peer memory: one tiny kernel, payload then flag (the slot engine does it inside its own launch)
+        k_exchange_send_t<PeerPtrs><<<1, 256, 0, (cudaStream_t)stream>>>(partial, (int)rec, pp, x.world, (unsigned long long)epoch);
+        ctx->launches++;
+    }
     CU(cudaGetLastError());
     return BGLS_OK;
 }
@@ -1914,13 +1939,25 @@ int bgls_final_exp_exchanged_dev(bgls_ctx* ctx, int curve, int lane, uint64_t ep
     void* work;
     int rc = dev_work(ctx, sl.s, mach_work_for(curve, x.world), &work);
     if (rc) return rc;
-    k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)(x.local + xch_flag_off(x, lane, parity, 0)), x.world,
-                                                         (unsigned long long)epoch, x.d_err);
-    ctx->launches++;
-    rc = finish_bytes_dev(ctx, curve, x.local + xch_rec_off(x, lane, parity, 0, rec), x.world, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream);
+    const unsigned long long* flags = (const unsigned long long*)(x.local + xch_flag_off(x, lane, parity, 0));
+    const XchWait xw{flags, (unsigned long long)epoch, x.d_err};
+    // throughput regime: wait, product and final exponentiation are ONE launch (k_slot_finish_bytes); otherwise wait kernel,
+    // the machine's import / tree / finish, guard kernel
+    const bool slot_path = d_is_identity && !ctx->thread_engine && (size_t)x.world <= SLOT_FANIN &&
+                           (ctx->engine == ENGINE_SLOT || (ctx->engine == ENGINE_AUTO && busy_estimate(ctx) >= SLOT_MIN_BUSY));
+    if (!slot_path) {
+        k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>(flags, x.world, (unsigned long long)epoch, x.d_err);
+        ctx->launches++;
+    }
+    bool fused = false;
+    rc = finish_bytes_dev(ctx, curve, x.local + xch_rec_off(x, lane, parity, 0, rec), x.world, 1, d_out_gt, d_is_identity, work, (cudaStream_t)stream,
+                          slot_path ? &xw : nullptr, &fused);
     if (rc) return rc;
-    k_exchange_guard<<<1, 1, 0, (cudaStream_t)stream>>>(x.d_err, (int*)d_is_identity);   // timed-out wait -> verdict false
-    ctx->launches++;
+    if (slot_path && !fused) return fail(ctx, BGLS_ERR_ARG, "exchange: engine choice changed between the wait and the finish");
+    if (!fused) {
+        k_exchange_guard<<<1, 1, 0, (cudaStream_t)stream>>>(x.d_err, (int*)d_is_identity);   // timed-out wait -> verdict false
+        ctx->launches++;
+    }
     CU(cudaGetLastError());
     return BGLS_OK;
 }

@@ -397,6 +397,11 @@ template <class F> struct MachFinisher {   // tail of k_slot_miller (slotvm.cuh)
     static constexpr size_t SMEM_BYTES = (size_t)F::NS * F::L * sizeof(uint32_t);
     static constexpr int MACH_L = F::L;
     __device__ __forceinline__ static void run(uint32_t* sm, const Args& a, const uint32_t* in) { mach_finish_warp<F>(sm, a, in); }
+    __device__ __forceinline__ static const uint8_t* wire_bytes(const Args& a) { return a.out_gt; }
+    __device__ __forceinline__ static void force_false(const Args& a) {
+        if (a.flag32) *a.flag32 = 0;
+        if (a.flag8) *a.flag8 = 0;
+    }
     __device__ __forceinline__ static Args for_product(Args a, uint8_t* flags8, size_t c) {   // product c of a batch
         a.out_gt = nullptr;
         a.flag32 = nullptr;

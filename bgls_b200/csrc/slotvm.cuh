@@ -283,6 +283,17 @@ struct SvNoFinish {
     static constexpr size_t SMEM_BYTES = 0;
     __device__ __forceinline__ static void run(uint32_t*, const Args&, const uint32_t*) {}
     __device__ __forceinline__ static Args for_product(const Args& a, uint8_t*, size_t) { return a; }
+    __device__ __forceinline__ static const uint8_t* wire_bytes(const Args&) { return nullptr; }
+    __device__ __forceinline__ static void force_false(const Args&) {}
+};
+// Multi-GPU exchange fused into the launch (bgls_miller_product_exchange_dev): the block that ends up with the product
+// stores its wire-form value into a mailbox on every peer over NVLink peer memory, fences, and raises the epoch flags --
+// the per-GPU partial leaves for the other ranks from inside the kernel that computed it.  world == 0: no exchange.
+struct SvPeers {
+    uint8_t* slot[8];
+    unsigned long long* flag[8];
+    int world, nbytes;
+    unsigned long long epoch;
 };
 // Batch of independent products in one launch (throughput mode, BASELINE config 5): product c covers the pairs
 // [off[c], off[c+1]).  k_slot_plan lays the blocks, tree levels and tickets of every product out (prefix sums); block b of
@@ -342,7 +353,7 @@ template <class C, class T, int WPB, class FIN>
 __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
                                                           size_t n, uint32_t* __restrict__ partials, unsigned* __restrict__ counters,
                                                           uint32_t* __restrict__ mach_out, int mach_l, typename FIN::Args fin,
-                                                          SvBatch batch, unsigned long long* __restrict__ trace) {
+                                                          SvBatch batch, unsigned long long* __restrict__ trace, SvPeers peers) {
     constexpr int N = C::N, FB = C::FP_BYTES, G = T::G, K = T::K, NPB = WPB * 32 / G, W4 = 2 * N / 4;
     extern __shared__ uint4 sv_sm[];
     // ---- which product, which block of it
@@ -480,6 +491,21 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
         __threadfence_block();
         __syncthreads();
         if (threadIdx.x < 32) FIN::run((uint32_t*)sv_sm, fin, mach_out);
+        if (peers.world > 0) {   // FIN exported the wire bytes: payload to every peer, then the flags
+            __threadfence();
+            __syncthreads();
+            const uint8_t* src = FIN::wire_bytes(fin);
+            for (int idx = threadIdx.x; idx < peers.world * peers.nbytes; idx += blockDim.x) {
+                const int r = idx / peers.nbytes, b = idx % peers.nbytes;
+                peers.slot[r][b] = src[b];
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < peers.world) {
+                *(volatile unsigned long long*)peers.flag[threadIdx.x] = peers.epoch;
+                __threadfence_system();
+            }
+        }
     }
 }
 
@@ -488,8 +514,9 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
 // exponentiation and the comparison with the identity, or the plain export.  Replaces import + tree + finish (three
 // dependent launches per step, which cost the multi-GPU pipeline a tenth of its throughput).
 template <class C, class T, int WPB, class FIN>
-__global__ void __launch_bounds__(WPB * 32) k_slot_finish_bytes(SvTables tb, const uint8_t* __restrict__ vals, int k, uint32_t* __restrict__ mach_out,
-                                                                int mach_l, typename FIN::Args fin) {
+__global__ void __launch_bounds__(WPB * 32) k_slot_finish_bytes(SvTables tb, const uint8_t* vals, int k, uint32_t* __restrict__ mach_out,
+                                                                int mach_l, typename FIN::Args fin, const unsigned long long* wait_flags,
+                                                                unsigned long long epoch, int* err) {
     constexpr int N = C::N, FB = C::FP_BYTES, G = T::G, NPB = WPB * 32 / G, W4 = 2 * N / 4, GPW = 32 / G;
     extern __shared__ uint4 sv_sm[];
     SvU4* consts = (SvU4*)sv_sm;
@@ -498,12 +525,26 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_finish_bytes(SvTables tb, con
     const int lane = threadIdx.x & 31;
     const int q = (threadIdx.x >> 5) * GPW + lane % GPW, gl = lane / GPW;
     const SlotFile<C, NPB> sf{slots, consts, q, 0};
+    if (wait_flags) {   // peer-memory exchange: the k values are the mailbox records of the ranks; wait (bounded) for their flags
+        if ((int)threadIdx.x < k) {
+            const volatile unsigned long long* f = wait_flags + threadIdx.x;
+            long long spins = 0;
+            while (*f < epoch) {
+                if (++spins > (1ll << 27)) { *err = 1; break; }   // several seconds: a missing peer is an error, not a hung GPU
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+    }
     __syncthreads();
     // group q: F <- value 2q, G <- value 2q + 1.  Wire position t (coefficient t / 2 of sv_wire_slot, im before re).
     for (int t = gl; t < 24; t += G) {
         const int which = t / 12, w = t % 12, v = 2 * q + which;
         if (v < k) {
-            const LN<N> x = sv_fp_from_be<C>(vals + ((size_t)v * 12 + w) * FB);
+            uint8_t be[FB];
+            const volatile uint8_t* src = vals + ((size_t)v * 12 + w) * FB;   // written by peers: not through the read-only path
+            for (int i = 0; i < FB; i++) be[i] = src[i];
+            const LN<N> x = sv_fp_from_be<C>(be);
             sf.store_fp(sv_wire_slot<T>(w >> 1) + (which ? T::S_G00 - T::S_F00 : 0), (w & 1) ? 0 : 1, x);
         }
     }
@@ -516,6 +557,10 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_finish_bytes(SvTables tb, con
         __threadfence_block();
         __syncthreads();
         if (threadIdx.x < 32) FIN::run((uint32_t*)sv_sm, fin, mach_out);
+        if (wait_flags) {   // a wait that timed out: the verdict is false whatever the stale records multiplied to
+            __syncthreads();
+            if (threadIdx.x == 0 && *err) FIN::force_false(fin);
+        }
     }
 }
 

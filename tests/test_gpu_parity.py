@@ -445,14 +445,28 @@ def test_verify_multi_signature_entry_point(ctx, cid, c):
 
 
 @pytest.mark.parametrize("cid,c", CURVES)
-def test_peer_memory_exchange_single_rank(cid, c):
+@pytest.mark.parametrize("engine", ["auto", "slot"])
+def test_peer_memory_exchange_single_rank(cid, c, engine):
     """The peer-memory exchange path (bgls_exchange_*, bgls_miller_product_exchange_dev, bgls_final_exp_exchanged_dev)
-    with world = 1: mailbox, send kernel, flag wait and finish, several epochs on two lanes (both parities),
-    against PairingProduct on the same inputs."""
+    with world = 1: mailbox, send, flag wait and finish, several epochs on two lanes (both parities), against
+    PairingProduct on the same inputs.  engine = auto: separate send / wait / guard kernels around the machine;
+    engine = slot: the stores into the mailboxes close the Miller launch and the wait opens the finishing launch."""
+    import os
+
     import torch
 
     import bgls_b200
-    ctx2 = bgls_b200.Context(0)
+    old = os.environ.get("BGLS_ENGINE")
+    if engine == "slot":
+        os.environ["BGLS_ENGINE"] = "slot"
+    try:
+        ctx2 = bgls_b200.Context(0)
+    finally:
+        if engine == "slot":
+            if old is None:
+                del os.environ["BGLS_ENGINE"]
+            else:
+                os.environ["BGLS_ENGINE"] = old
     try:
         h = ctx2.exchange_create(1, 0, 2)
         ctx2.exchange_connect(0, h)

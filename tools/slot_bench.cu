@@ -49,7 +49,7 @@ int run(size_t n, int S, int reps) {
         CK(cudaEventRecord(e0, 0));
         for (int s = 0; s < S; s++) {
             CK(cudaStreamWaitEvent(st[s], e0, 0));
-            k_slot_miller<C, T, WPB, SvNoFinish><<<nb, WPB * 32, smem, st[s]>>>(tb, d1, d2, n, dlv + (size_t)s * lvw, dcnt + (size_t)s * ncnt, dmv + (size_t)s * 12 * 16, 0, SvNoFinish::Args{0}, SvBatch{}, nullptr);
+            k_slot_miller<C, T, WPB, SvNoFinish><<<nb, WPB * 32, smem, st[s]>>>(tb, d1, d2, n, dlv + (size_t)s * lvw, dcnt + (size_t)s * ncnt, dmv + (size_t)s * 12 * 16, 0, SvNoFinish::Args{0}, SvBatch{}, nullptr, SvPeers{});
         }
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
