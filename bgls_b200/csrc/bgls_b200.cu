@@ -948,6 +948,8 @@ template <class C, class T, class F> int upload_slot(bgls_ctx* ctx, SlotEngDev& 
     CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB, FIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB, SvNoFinish>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem_bytes<C, T, NPB>()));
     CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB, SvNoFinish>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB, SvWireFinisher<C, T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem_bytes<C, T, NPB>()));
+    CU(cudaFuncSetAttribute(k_slot_miller<C, T, SLOT_WPB, SvWireFinisher<C, T>>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_mach_finish_lean<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN::SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_mach_finish_lean<F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_slot_finish_bytes<C, T, SLOT_WPB, FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -994,6 +996,17 @@ int slot_pairing(bgls_ctx* ctx, const SlotEngDev& se, const MachDev& md, const u
     uint32_t* mval = (uint32_t*)((char*)levels + align_up((sv_tree_words(nb, SLOT_FANIN, C::N) + 1) * 4));
     MachFinishArgs fa{md.f, do_final ? md.finalexp : md.export_, do_final ? F::FINALEXP_LEN : F::EXPORT_LEN, d_out, d_flag, nullptr};
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], s);
+    if (!do_final) {
+        // raw Miller product (a shard of a multi-GPU verification): wire export by the slot engine itself, so the blocks carry
+        // no finisher footprint; the stores into the peers' mailboxes follow in the same launch when `peers` is given
+        using WF = SvWireFinisher<C, T>;
+        k_slot_miller<C, T, SLOT_WPB, WF><<<(unsigned)nb, SLOT_WPB * 32, sv_smem_bytes<C, T, NPB>(), s>>>(
+            se.tb, d_g1, d_g2, n, levels, tl_slot->tickets, mval, 0, typename WF::Args{d_out}, SvBatch{}, ctx->trace, peers ? *peers : SvPeers{});
+        ctx->launches++;
+        if (ctx->profiling) { cudaEventRecord(ctx->ev[1], s); cudaEventRecord(ctx->ev[2], s); }
+        CU(cudaGetLastError());
+        return BGLS_OK;
+    }
     if ((ctx->slot_split < 0 ? C::IS_BN : ctx->slot_split == 1) && !peers) {
         // Miller blocks without the finisher's shared-memory footprint (altbn128: 14 KB instead of 19 KB per one-warp block,
         // 15 instead of 11 resident blocks per SM), final exponentiation as a second one-warp launch: +5 % on altbn128,

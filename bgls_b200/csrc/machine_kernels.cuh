@@ -395,6 +395,7 @@ __device__ __forceinline__ void mach_finish_warp(uint32_t* sm, const MachFinishA
 template <class F> struct MachFinisher {   // tail of k_slot_miller (slotvm.cuh)
     using Args = MachFinishArgs;
     static constexpr size_t SMEM_BYTES = (size_t)F::NS * F::L * sizeof(uint32_t);
+    static constexpr bool HAS_TAIL = true;
     static constexpr int MACH_L = F::L;
     __device__ __forceinline__ static void run(uint32_t* sm, const Args& a, const uint32_t* in) { mach_finish_warp<F>(sm, a, in); }
     __device__ __forceinline__ static const uint8_t* wire_bytes(const Args& a) { return a.out_gt; }

@@ -281,9 +281,29 @@ __device__ __forceinline__ void sv_emit_value(SvU4* slots, const SvU4* consts, c
 struct SvNoFinish {
     struct Args { int unused; };
     static constexpr size_t SMEM_BYTES = 0;
+    static constexpr bool HAS_TAIL = false;
     __device__ __forceinline__ static void run(uint32_t*, const Args&, const uint32_t*) {}
     __device__ __forceinline__ static Args for_product(const Args& a, uint8_t*, size_t) { return a; }
     __device__ __forceinline__ static const uint8_t* wire_bytes(const Args&) { return nullptr; }
+    __device__ __forceinline__ static void force_false(const Args&) {}
+};
+// SvWireFinisher: the raw Miller product leaves as a GT wire record (12 big-endian field elements, w-powers 5,3,1,4,2,0,
+// im before re) -- what a rank sends to its peers.  No shared memory beyond the slot file.
+template <class C, class T> struct SvWireFinisher {
+    struct Args { uint8_t* out; };
+    static constexpr size_t SMEM_BYTES = 0;
+    static constexpr bool HAS_TAIL = true;
+    __device__ __forceinline__ static void run(uint32_t*, const Args& a, const uint32_t* in) {   // in: internal form, 12 N words
+        const int t = threadIdx.x;
+        if (t >= 12) return;
+        const int fi = 2 * (sv_wire_slot<T>(t >> 1) - T::S_F00) + ((t & 1) ? 0 : 1);
+        LN<C::N> v;
+#pragma unroll
+        for (int i = 0; i < C::N; i++) v.v[i] = in[fi * C::N + i];
+        sv_fp_to_be<C>(a.out + (size_t)t * C::FP_BYTES, v);
+    }
+    __device__ __forceinline__ static Args for_product(const Args& a, uint8_t*, size_t) { return a; }
+    __device__ __forceinline__ static const uint8_t* wire_bytes(const Args& a) { return a.out; }
     __device__ __forceinline__ static void force_false(const Args&) {}
 };
 // Multi-GPU exchange fused into the launch (bgls_miller_product_exchange_dev): the block that ends up with the product
@@ -487,7 +507,7 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_miller(SvTables tb, const uin
         count = groups;
     }
     sv_emit_value<C, T, NPB>(slots, consts, tb, mach_out, mach_l);
-    if (FIN::SMEM_BYTES) {   // the final exponentiation runs on the first warp of this block, over the same shared memory
+    if (FIN::HAS_TAIL) {   // the final exponentiation (or the export) runs on the first warp of this block, over the same shared memory
         __threadfence_block();
         __syncthreads();
         if (threadIdx.x < 32) FIN::run((uint32_t*)sv_sm, fin, mach_out);
@@ -553,7 +573,7 @@ __global__ void __launch_bounds__(WPB * 32) k_slot_finish_bytes(SvTables tb, con
     sv_run<C, NPB, G>(slots, consts, q, 0, tb.code, tb.offs[T::P_MUL12], tb.offs[T::P_MUL12 + 1], gl, 2 * q + 1 < k);
     sv_block_tree<C, T, NPB>(slots, consts, tb, q, gl, (k + 1) / 2);
     sv_emit_value<C, T, NPB>(slots, consts, tb, mach_out, mach_l);
-    if (FIN::SMEM_BYTES) {
+    if (FIN::HAS_TAIL) {
         __threadfence_block();
         __syncthreads();
         if (threadIdx.x < 32) FIN::run((uint32_t*)sv_sm, fin, mach_out);
