@@ -359,6 +359,14 @@ __global__ void __launch_bounds__(TB) k_hash_to_g1_bls(const uint8_t* __restrict
     }
 }
 
+// bls12-381, throughput form: one thread per message, one cofactor multiplication per message (hash.cuh)
+template <class C>
+__global__ void __launch_bounds__(TB) k_hash_to_g1_bls_one(const uint8_t* __restrict__ msgs, const unsigned long long* __restrict__ off, size_t n,
+                                                           uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i < n) hash_to_g1_ft_shared_cofactor<C>(out + i * 2 * C::FP_BYTES, msgs + off[i], (size_t)(off[i + 1] - off[i]));
+}
+
 // ---------------------------------------------------------------- peer-memory exchange of the per-GPU partials
 // Every rank stores its 12F-byte Miller product straight into a mailbox on each peer (NVLink peer memory mapped
 // through CUDA IPC) and then raises that mailbox's epoch flag; the finishing side waits for the flags of all ranks.
@@ -1670,8 +1678,13 @@ static int hash_dev(bgls_ctx* ctx, int curve, const void* d_msgs, const void* d_
             k_hash_to_g1_bn_pool<BN254><<<(unsigned)((n + 31) / 32), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
         else
             k_hash_to_g1_bn<BN254><<<(unsigned)((n * 8 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
-    } else
-        k_hash_to_g1_bls<BLS381><<<(unsigned)((n * 2 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    } else {
+        const bool pool = ctx->hash_mode == 1 || (ctx->hash_mode == 0 && n >= 64 && (busy_estimate(ctx) >= 3 || n >= 16384));
+        if (pool)
+            k_hash_to_g1_bls_one<BLS381><<<(unsigned)((n + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+        else
+            k_hash_to_g1_bls<BLS381><<<(unsigned)((n * 2 + TB - 1) / TB), TB, 0, s>>>((const uint8_t*)d_msgs, (const unsigned long long*)d_off, n, (uint8_t*)d_out);
+    }
     ctx->launches++;
     CU(cudaGetLastError());
     return BGLS_OK;

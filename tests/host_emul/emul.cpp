@@ -241,3 +241,5 @@ extern "C" int emu_decompress(int curve, int group, const uint8_t* in, int check
     if (curve == 0) return group == 1 ? decompress_g1<BN254>(rec, in, check_subgroup) : decompress_g2<BN254>(rec, in, check_subgroup);
     return group == 1 ? decompress_g1<BLS381>(rec, in, check_subgroup) : decompress_g2<BLS381>(rec, in, check_subgroup);
 }
+// throughput form of the bls12-381 hash (one cofactor multiplication for both halves)
+extern "C" void emu_hash_to_g1_shared_cofactor(const uint8_t* msg, size_t len, uint8_t* out) { hash_to_g1_ft_shared_cofactor<BLS381>(out, msg, len); }

@@ -213,6 +213,38 @@ def test_hash_to_g1_reference_vectors_gpu(ctx, cid, c):
         assert got[i * rec:(i + 1) * rec] == w, i
 
 
+def test_bls12_throughput_hash_equals_latency_hash(ctx):
+    """bls12-381 HashToG1 in its throughput form (k_hash_to_g1_bls_one: one cofactor multiplication per message) against
+    the two-lanes-per-message form and the reference vectors."""
+    import base64
+    import os
+    import bgls_b200
+    cid, c = CURVES[1]
+    old = os.environ.get("BGLS_HASH")
+    os.environ["BGLS_HASH"] = "pool"
+    try:
+        pctx = bgls_b200.Context(0)
+    finally:
+        if old is None:
+            del os.environ["BGLS_HASH"]
+        else:
+            os.environ["BGLS_HASH"] = old
+    try:
+        msgs, want = [], []
+        for line in open(os.path.join(os.path.dirname(__file__), "golden", "bls12G1Hash.dat")):
+            m, pt = line.strip().split(",")
+            msgs.append(base64.b64decode(m))
+            want.append(base64.b64decode(pt))
+        rng = random.Random(43)
+        msgs += [bytes(rng.randrange(256) for _ in range(rng.choice((0, 1, 31, 64, 124, 128, 200)))) for _ in range(300)]
+        got = pctx.hash_to_g1(cid, msgs)
+        for i, w in enumerate(want):
+            assert got[96 * i:96 * (i + 1)] == w, i
+        assert got == ctx.hash_to_g1(cid, msgs)
+    finally:
+        pctx.close()
+
+
 def test_pooled_try_and_increment_is_the_sequential_loop():
     """altbn128 HashToG1 in its throughput form (k_hash_to_g1_bn_pool: a warp re-deals its lanes over the messages
     still open every round) finds the counter the sequential loop of curves/hash.go:53-77 finds: reference vectors,

@@ -160,6 +160,13 @@ def test_hash_to_g1_reference_vectors(E, cid, c):
     for ln in (0, 1, 31, 32, 123, 124, 127, 128, 135, 136, 137, 200, 300):
         m = bytes(rng.randrange(256) for _ in range(ln))
         assert H(m) == c.marshal_g1(c.hash_to_g1(m)), ln
+    if cid == 1:   # throughput form: one cofactor multiplication for both halves (h Q0 + h Q1 = h (Q0 + Q1))
+        E.emu_hash_to_g1_shared_cofactor.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+        msgs = [base64.b64decode(line.split(",")[0]) for line in open(os.path.join(HERE, "golden", fname))] + [b"", b"x" * 200]
+        for m in msgs:
+            out = ctypes.create_string_buffer(2 * nb)
+            E.emu_hash_to_g1_shared_cofactor(m, len(m), out)
+            assert out.raw == H(m)
 
 
 @pytest.mark.parametrize("cid,c", CURVES)
