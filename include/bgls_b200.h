@@ -77,7 +77,8 @@ int bgls_pair(bgls_ctx* ctx, int curve, const uint8_t* g1, const uint8_t* g2, ui
 int bgls_gt_mul(bgls_ctx* ctx, int curve, const uint8_t* a, const uint8_t* b, uint8_t* out_gt);
 
 /* AggregatePoints -- curves/curve.go:73-110 (also AggregateSignatures / AggregateKeys,
- * bgls/bgls.go:123-131).  n >= 1; n == 0 returns BGLS_ERR_ARG (the reference never returns). */
+ * bgls/bgls.go:123-131).  n >= 1; n == 0 returns BGLS_ERR_ARG (the reference never returns).  Records at infinity,
+ * repeated points and cancelling points are all legal inputs (complete addition formulas); coordinates must be < q. */
 int bgls_aggregate_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, size_t n, uint8_t* out);
 
 /* ScalePoints / Point.Mul -- curves/curve.go:190-214; altbn128.go:107-121,235-249.
@@ -87,8 +88,10 @@ int bgls_scale_points(bgls_ctx* ctx, int curve, int group, const uint8_t* pts, c
 
 /* CurveSystem.HashToG1 -- curves/altbn128.go:509-513 (Keccak-256 try-and-increment, curves/hash.go:53-77) and
  * curves/bls12_381.go:349-351 (blake2b + Fouque-Tibouchi + cofactor, curves/hash.go:79-167): the pre-step of
- * verifyAggSig (bgls/bgls.go:106-111), one message per GPU thread.  Message i is msgs[offsets[i] .. offsets[i+1]);
- * out receives n uncompressed G1 records. */
+ * verifyAggSig (bgls/bgls.go:106-111).  Message i is msgs[offsets[i] .. offsets[i+1]); out receives n uncompressed G1
+ * records.  Two forms per curve, chosen by load (same bytes either way): a latency form (several lanes per message) and a
+ * throughput form (altbn128: the lanes of a warp are re-dealt over the messages still open every round; bls12-381: one
+ * cofactor multiplication for both halves of a message). */
 int bgls_hash_to_g1(bgls_ctx* ctx, int curve, const uint8_t* msgs, const uint64_t* offsets, size_t n, uint8_t* out);
 
 /* Signer-set sharding: product of the *Miller values* of n pairs without the
